@@ -1,0 +1,281 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of BASELINE.json:
+
+  metric  audio-sec/sec, E6D2 training step (encoder LSTM stack -> predictor -> joint -> rnnt_loss,
+          forward + backward + Adam), B=32 per GPU, T=1000 frames (37.5 ms each), U=128, V=1024.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  torchrun --nproc-per-node N bench.py --gpus N ...        (one rank per GPU, NCCL)
+
+"ours": the B200 engine in bf16 mode (tcgen05 GEMMs, fp32 accumulate / fp32 recurrent state),
+weak scaling (B=32 per GPU), one all-reduce of the flat gradient bucket per step.
+"reference": the reference's own CPU path restated in oracle/model_torch.py (torch-CPU fp32,
+nn.LSTM's ATen kernel) + the reference's compiled warp-transducer CPU library (oracle/_ref) --
+a bounded sample of the same workload on the host cores.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FRAME_SEC = 0.0375          # E6D2: downsample 3 x hop 200 / 16 kHz (flagfiles/E6D2.txt:28,31)
+E6D2 = dict(vocab_embed_size=64, vocab_size=1024, input_size=240, enc_hidden_size=1024, enc_layers=6,
+            enc_dropout=0.0, enc_proj_size=640, dec_hidden_size=256, dec_layers=2, dec_dropout=0.0,
+            dec_proj_size=256, joint_size=640)
+B, T, U, V = 32, 1000, 128, 1024
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sus=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sus=1400.0, src="fallback")
+
+
+class ClockSampler:
+    FIELDS = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        if not sm:
+            return None
+        reasons = []
+        for i, name in enumerate(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")):
+            if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx) if mx else None, reasons=reasons, samples=len(sm))
+
+
+def run_ours(args):
+    import torch
+    from edgedict_b200 import dist as ed
+    from edgedict_b200 import ops
+    from edgedict_b200.optim import FlatAdam
+    from edgedict_b200.rnnt.models import Transducer
+    from edgedict_b200._lib import lib
+    lib()                                             # fail loudly if the CUDA library is missing
+    rank, world, local = ed.init_from_env("nccl")
+    assert world == args.gpus, "launch with torchrun --nproc-per-node %d" % args.gpus
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    torch.manual_seed(10)
+    model = Transducer(**E6D2).to(dev)
+    model.set_precision(args.precision)
+    opt = FlatAdam(model, lr=5e-4)
+    ed.broadcast_bucket(opt.flat_params)
+    g = torch.Generator(device=dev).manual_seed(10 + rank)
+    xs = torch.randn(B, T, 240, device=dev, generator=g)
+    ys = torch.randint(4, V, (B, U), device=dev, dtype=torch.int32, generator=g)
+    xlen = torch.full((B,), T, dtype=torch.int32)
+    ylen = torch.full((B,), U, dtype=torch.int32)
+    # pinned host copies for the end-to-end leg
+    hx, hy = xs.cpu().pin_memory(), ys.cpu().pin_memory()
+    hloss = torch.zeros(1).pin_memory()
+
+    def step(x, y):
+        opt.zero_grad()
+        loss = model(x, y, xlen, ylen)
+        loss.backward()
+        ed.allreduce_bucket(opt.flat_grads, world)
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        loss = step(xs, ys)
+    barrier()
+    first_loss = float(loss)
+
+    # ---- leg 1: inputs resident in HBM, per-kernel events on --------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ops.PROF.reset()
+    ops.PROF.enabled = True
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = step(xs, ys)
+    e1.record()
+    barrier()
+    ms_dev = ed.max_over_ranks(e0.elapsed_time(e1), dev) / args.steps
+    prof = ops.PROF.summary()
+    launches = ops.PROF.launches // args.steps
+    ops.PROF.enabled = False
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- leg 2: end to end through the public API with host buffers --------------------------------
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        x = hx.to(dev, non_blocking=True)
+        y = hy.to(dev, non_blocking=True)
+        loss = step(x, y)
+        hloss.copy_(loss.detach(), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    e1.record()
+    barrier()
+    ms_e2e = ed.max_over_ranks(e0.elapsed_time(e1), dev) / args.steps
+    last_loss = float(hloss)
+
+    if rank != 0:
+        return None
+    pk = peaks()
+    audio = world * B * T * FRAME_SEC
+    kern = {}
+    for name, d in prof.items():
+        ms = d["ms"] / args.steps
+        kern[name] = dict(ms_per_step=round(ms, 4), calls_per_step=d["calls"] / args.steps,
+                          share=round(ms / ms_dev, 4),
+                          gbs=round(d["bytes"] / args.steps / ms / 1e6, 1) if d["bytes"] else None,
+                          tflops=round(d["flops"] / args.steps / ms / 1e9, 2) if d["flops"] else None)
+    top = max(kern, key=lambda k: kern[k]["ms_per_step"])
+    hbm_kernels = ("rnnt_loss_bwd", "rnnt_loss_fwd")
+    if top in hbm_kernels:
+        ach = kern[top]["gbs"]
+        roof = dict(kernel=top, bound="hbm", achieved=ach, peak=pk["hbm"], unit="GB/s", frac=round(ach / pk["hbm"], 4))
+    else:
+        ach = kern[top]["tflops"] or 0.0
+        roof = dict(kernel=top, bound="tensor", achieved=ach, peak=pk["tf_sus"], unit="TFLOP/s",
+                    frac=round(ach / pk["tf_sus"], 4))
+    roof["traffic"] = None
+    roof["peak_source"] = pk["src"] + (" (sustained)" if roof["bound"] == "tensor" else "")
+    # the BASELINE.json side metric: joint+loss HBM fraction on 3*s*N algorithmic bytes
+    n_logits = B * (T // 2) * (U + 1) * V
+    jl_ms = sum(kern[k]["ms_per_step"] for k in hbm_kernels if k in kern)
+    jl_bytes = (4 + 4 + (2 if args.precision == "bf16" else 4)) * n_logits
+    joint_loss = dict(algorithmic_gb=round(jl_bytes / 1e9, 2), ms=round(jl_ms, 3),
+                      gbs=round(jl_bytes / jl_ms / 1e6, 1), frac_hbm=round(jl_bytes / jl_ms / 1e6 / pk["hbm"], 4))
+    out = dict(metric="audio-sec/sec E6D2 B=32 T=1000 U=128 V=1024 training step", value=round(audio / ms_dev * 1e3, 1),
+               unit="audio-sec/sec", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+               ms_per_step=round(ms_dev, 3), higher_is_better=True, scaling="weak", vs_baseline=None,
+               dtype="bf16" if args.precision == "bf16" else "f32", data="synthetic",
+               config=dict(workload="E6D2 (6x1024 LSTM enc / 2x256 pred / joint 640 / V=1024) fwd+loss+bwd+Adam, "
+                                    "B=32/GPU T=1000 U=128 (configs[1]); frame=37.5 ms",
+                           global_batch=B * world, seq_len=T, parallelism="dp%d" % world,
+                           l2="inputs >> L2: 8.45 GB of logits streamed per step"),
+               e2e=dict(value=round(audio / ms_e2e * 1e3, 1), unit="audio-sec/sec",
+                        h2d_bytes_per_step=hx.numel() * 4 + hy.numel() * 4, d2h_bytes_per_step=4,
+                        ms_per_step=round(ms_e2e, 3)),
+               gpu_launches=launches, clocks=clocks, roofline=roof, joint_loss_hbm=joint_loss, kernels=kern,
+               loss_first=round(first_loss, 4), loss_last=round(last_loss, 4))
+    return out
+
+
+def cpu_sample_shape(total_steps):
+    if total_steps <= 4:
+        return 2, 1000, 128
+    if total_steps <= 12:
+        return 1, 500, 64
+    return 1, 250, 32
+
+
+def run_reference(steps, warmup, timed_only=False):
+    """The reference's CPU path (oracle port of rnnt/models.py + compiled warp-transducer CPU loss)."""
+    import torch
+    from oracle import loss as ol
+    from oracle import model_torch as mt
+    from edgedict_b200.rnnt.models import Transducer          # parameter container only (same init)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    torch.manual_seed(10)
+    shell = Transducer(**E6D2)
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in shell.state_dict().items()}
+    optim = torch.optim.Adam(list(sd.values()), lr=5e-4)
+    Bs, Ts, Us = cpu_sample_shape(steps + warmup)
+    torch.manual_seed(10)
+    xs = torch.randn(Bs, Ts, 240)
+    ys = torch.randint(4, V, (Bs, Us), dtype=torch.int32)
+    xlen, ylen = torch.full((Bs,), Ts, dtype=torch.int32), torch.full((Bs,), Us, dtype=torch.int32)
+
+    def one():
+        optim.zero_grad()
+        loss = mt.transducer_loss(sd, xs, ys, xlen, ylen, fast=True, use_ref=True)
+        loss.backward()
+        optim.step()
+        return float(loss.detach())
+
+    for _ in range(warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    dt = (time.perf_counter() - t0) / steps
+    val = Bs * Ts * FRAME_SEC / dt
+    kind = "reference" if ol.have_ref() else "port"
+    sample = "B=%d T=%d U=%d V=1024 E6D2 fwd+loss+bwd+Adam fp32, %d step(s)" % (Bs, Ts, Us, steps)
+    return dict(value=round(val, 3), unit="audio-sec/sec", cores=cores,
+                kind=kind + " (warp-transducer CPU lib compiled from the reference; model = torch-CPU port "
+                            "calling the same ATen LSTM kernel as nn.LSTM)", sample=sample), dt
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cb, dt = run_reference(args.steps, args.warmup)
+        print(json.dumps(dict(impl="reference", metric="audio-sec/sec E6D2 B=32 T=1000 U=128 V=1024 training step",
+                              value=cb["value"], unit="audio-sec/sec", n_gpus=args.gpus, steps=args.steps,
+                              warmup=args.warmup, ms_per_step=round(dt * 1e3, 1), higher_is_better=True,
+                              scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                              config=dict(workload="E6D2 training step on host cores, bounded sample: " + cb["sample"]),
+                              cpu_baseline=cb, gpu_launches=0,
+                              e2e=dict(value=cb["value"], unit="audio-sec/sec", h2d_bytes_per_step=0,
+                                       d2h_bytes_per_step=0))))
+        return
+    out = run_ours(args)
+    if out is None:
+        return
+    if args.gpus == 1 and not args.no_cpu_baseline:
+        cb, _ = run_reference(1, 1)
+        out["cpu_baseline"] = cb
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

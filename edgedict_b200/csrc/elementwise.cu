@@ -1,0 +1,484 @@
+// elementwise.cu -- bandwidth-bound glue kernels of the RNN-T path (sm_100a).
+//
+//   layernorm fwd/bwd (+ fused residual add)      nn.LayerNorm in rnnt/models.py:47,124 and the
+//                                                 `xs = xs + xs_next` of rnnt/models.py:66-69
+//   time reduction fwd/bwd                        TimeReduction.forward, rnnt/models.py:21-29
+//   embedding gather / scatter-add (BOS prepend)  Decoder.forward, rnnt/models.py:150-153
+//   joint hidden tanh(e_t + d_u) fwd/bwd          Joint.forward, rnnt/models.py:169-179 with the
+//                                                 first Linear split as W1e*e + W1d*d + b1
+//   column sums (bias gradients), casts, Adam     torch autograd / torch.optim.Adam in
+//                                                 cli/baseline.py:141-156,239-245
+#include "common.cuh"
+#include "../../include/edgedict_b200.h"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, H <= 32*MAXV*... generic loop; two-pass mean/var in registers
+// when the row fits (H <= 2048), otherwise three passes over global.
+// ------------------------------------------------------------------------------------------
+constexpr int LN_WARPS = 8;
+
+template <int PL>   // PL = values per lane kept in registers; H <= 32*PL
+__global__ void __launch_bounds__(LN_WARPS * 32)
+layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ res,
+                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                     float* __restrict__ y, __nv_bfloat16* __restrict__ y16,
+                     float* __restrict__ mean, float* __restrict__ rstd, long rows, int H, float eps) {
+    const int lane = threadIdx.x & 31;
+    const long wstride = (long)gridDim.x * LN_WARPS;
+    for (long r = (long)blockIdx.x * LN_WARPS + (threadIdx.x >> 5); r < rows; r += wstride) {
+        const float* xr = x + r * H;
+        const float* rr = res ? res + r * H : nullptr;
+        float v[PL];
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < PL; ++i) {
+            int c = lane + i * 32;
+            v[i] = 0.f;
+            if (c < H) {
+                float t = xr[c];
+                if (rr) t += rr[c];
+                v[i] = t;
+                s += t;
+            }
+        }
+        const float mu = warp_sum(s) / H;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < PL; ++i) {
+            int c = lane + i * 32;
+            if (c < H) { float d = v[i] - mu; q += d * d; }
+        }
+        const float rs = rsqrtf(warp_sum(q) / H + eps);
+        if (lane == 0) {
+            if (mean) mean[r] = mu;
+            if (rstd) rstd[r] = rs;
+        }
+#pragma unroll
+        for (int i = 0; i < PL; ++i) {
+            int c = lane + i * 32;
+            if (c < H) {
+                float o = (v[i] - mu) * rs * gamma[c] + beta[c];
+                y[r * H + c] = o;
+                if (y16) y16[r * H + c] = __float2bfloat16(o);
+            }
+        }
+    }
+}
+
+// dz = rstd * (g - mean(g) - xhat * mean(g*xhat)), g = dy*gamma
+template <int PL>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                     const float* __restrict__ res, const float* __restrict__ gamma,
+                     const float* __restrict__ mean, const float* __restrict__ rstd,
+                     float* __restrict__ dz, long rows, int H) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const long wstride = (long)gridDim.x * LN_WARPS;
+    for (long r = (long)blockIdx.x * LN_WARPS + w; r < rows; r += wstride) {
+        const float mu = mean[r], rs = rstd[r];
+        float xh[PL], g[PL];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < PL; ++i) {
+            int c = lane + i * 32;
+            xh[i] = 0.f; g[i] = 0.f;
+            if (c < H) {
+                float z = x[r * H + c];
+                if (res) z += res[r * H + c];
+                xh[i] = (z - mu) * rs;
+                g[i] = dy[r * H + c] * gamma[c];
+                s1 += g[i];
+                s2 += g[i] * xh[i];
+            }
+        }
+        s1 = warp_sum(s1) / H;
+        s2 = warp_sum(s2) / H;
+#pragma unroll
+        for (int i = 0; i < PL; ++i) {
+            int c = lane + i * 32;
+            if (c < H) dz[r * H + c] = rs * (g[i] - s1 - xh[i] * s2);
+        }
+    }
+}
+
+// dgamma[c] += sum_r dy*xhat ; dbeta[c] += sum_r dy   (thread per column, rows chunked over grid.y)
+__global__ void layernorm_param_grad_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                            const float* __restrict__ res,
+                                            const float* __restrict__ mean,
+                                            const float* __restrict__ rstd, float* __restrict__ dgamma,
+                                            float* __restrict__ dbeta, long rows, int H,
+                                            long rows_per_block) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= H) return;
+    long r0 = (long)blockIdx.y * rows_per_block;
+    long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+    float ag = 0.f, ab = 0.f;
+    for (long r = r0; r < r1; ++r) {
+        float z = x[r * H + c];
+        if (res) z += res[r * H + c];
+        float d = dy[r * H + c];
+        ag += d * (z - mean[r]) * rstd[r];
+        ab += d;
+    }
+    atomicAdd(dgamma + c, ag);
+    atomicAdd(dbeta + c, ab);
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void time_reduce_fwd_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                       __nv_bfloat16* __restrict__ y16, int B, int T, int H) {
+    const int T2 = (T + 1) / 2;
+    const long n = (long)B * T2 * H;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        int c = (int)(i % H);
+        long bt = i / H;
+        int t2 = (int)(bt % T2);
+        int b = (int)(bt / T2);
+        float a = x[((long)b * T + 2 * t2) * H + c];
+        float bb = (2 * t2 + 1 < T) ? x[((long)b * T + 2 * t2 + 1) * H + c] : 0.f;   // zero pad
+        float o = (a + bb) * 0.5f;
+        y[i] = o;
+        if (y16) y16[i] = __float2bfloat16(o);
+    }
+}
+__global__ void time_reduce_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int B,
+                                       int T, int H) {
+    const int T2 = (T + 1) / 2;
+    const long n = (long)B * T * H;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        int c = (int)(i % H);
+        long bt = i / H;
+        int t = (int)(bt % T);
+        int b = (int)(bt / T);
+        dx[i] = 0.5f * dy[((long)b * T2 + t / 2) * H + c];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Embedding.  ids [B,U] (int32 or int64); out [B,U+prepend,E]; position 0 = BOS row if prepend.
+// ------------------------------------------------------------------------------------------
+template <typename I>
+__global__ void embedding_fwd_kernel(const I* __restrict__ ids, const float* __restrict__ W,
+                                     float* __restrict__ out, __nv_bfloat16* __restrict__ out16,
+                                     int B, int U, int E, int prepend, int bos) {
+    const int U1 = U + prepend;
+    const long n = (long)B * U1 * E;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        int e = (int)(i % E);
+        long bu = i / E;
+        int u = (int)(bu % U1);
+        int b = (int)(bu / U1);
+        long id = (prepend && u == 0) ? bos : (long)ids[(long)b * U + u - prepend];
+        float v = W[id * E + e];
+        out[i] = v;
+        if (out16) out16[i] = __float2bfloat16(v);
+    }
+}
+template <typename I>
+__global__ void embedding_bwd_kernel(const I* __restrict__ ids, const float* __restrict__ dout,
+                                     float* __restrict__ dW, int B, int U, int E, int prepend,
+                                     int bos, int pad) {
+    const int U1 = U + prepend;
+    const long n = (long)B * U1 * E;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        int e = (int)(i % E);
+        long bu = i / E;
+        int u = (int)(bu % U1);
+        int b = (int)(bu / U1);
+        long id = (prepend && u == 0) ? bos : (long)ids[(long)b * U + u - prepend];
+        if (id != pad) atomicAdd(dW + id * E + e, dout[i]);    // padding_idx row gets no gradient
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Joint hidden: h[b,t,u,:] = tanh(ep[b,t,:] + dp[b,u,:])   (ep already carries b1)
+// one CTA per (b,t): ep row staged in registers, loops over u; J % 4 == 0 fast path.
+// ------------------------------------------------------------------------------------------
+template <typename TO>
+__device__ __forceinline__ void store_h(TO* p, float v);
+template <> __device__ __forceinline__ void store_h<float>(float* p, float v) { *p = v; }
+template <> __device__ __forceinline__ void store_h<__nv_bfloat16>(__nv_bfloat16* p, float v) {
+    *p = __float2bfloat16(v);
+}
+
+template <typename TO>
+__global__ void joint_hidden_fwd_kernel(const float* __restrict__ ep, const float* __restrict__ dp,
+                                        TO* __restrict__ hid, int B, int T, int U, int J) {
+    const long bt = blockIdx.x;
+    const int b = (int)(bt / T);
+    const float* e = ep + bt * J;
+    const float* d = dp + (long)b * U * J;
+    TO* o = hid + bt * (long)U * J;
+    const int n = U * J;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        int j = i % J;
+        store_h<TO>(o + i, tanhf(e[j] + d[i]));
+    }
+}
+
+// dpre = dh * (1 - h^2) written in place over dh; dep[b,t,:] = sum_u dpre
+template <typename TH>
+__global__ void joint_hidden_bwd_t_kernel(TH* __restrict__ dh, const TH* __restrict__ hid,
+                                          float* __restrict__ dep, int T, int U, int J) {
+    const long bt = blockIdx.x;
+    TH* g = dh + bt * (long)U * J;
+    const TH* h = hid + bt * (long)U * J;
+    for (int j = threadIdx.x; j < J; j += blockDim.x) {
+        float acc = 0.f;
+        for (int u = 0; u < U; ++u) {
+            float hv = (float)h[(long)u * J + j];
+            float p = (float)g[(long)u * J + j] * (1.f - hv * hv);
+            g[(long)u * J + j] = (TH)p;
+            acc += p;
+        }
+        dep[bt * J + j] = acc;
+    }
+}
+// ddp[b,u,:] = sum_t dpre[b,t,u,:]   one CTA per (b,u)
+template <typename TH>
+__global__ void joint_hidden_bwd_u_kernel(const TH* __restrict__ dpre, float* __restrict__ ddp,
+                                          int T, int U, int J) {
+    const int b = blockIdx.x / U, u = blockIdx.x % U;
+    const TH* g = dpre + ((long)b * T * U + u) * J;
+    for (int j = threadIdx.x; j < J; j += blockDim.x) {
+        float acc = 0.f;
+        for (int t = 0; t < T; ++t) acc += (float)g[(long)t * U * J + j];
+        ddp[((long)b * U + u) * J + j] = acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// column sums out[c] (+)= sum_r x[r,c]; grid (colblocks, rowblocks), atomics across rowblocks
+// ------------------------------------------------------------------------------------------
+template <typename TI>
+__global__ void colsum_kernel(const TI* __restrict__ x, float* __restrict__ out, long rows, int N,
+                              long rows_per_block) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= N) return;
+    long r0 = (long)blockIdx.y * rows_per_block;
+    long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+    float acc = 0.f;
+    for (long r = r0; r < r1; ++r) acc += (float)x[r * N + c];
+    atomicAdd(out + c, acc);
+}
+
+__global__ void cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long n) {
+    long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const long stride = (long)gridDim.x * blockDim.x * 4;
+    for (; i + 3 < n; i += stride) {
+        float4 v = *reinterpret_cast<const float4*>(x + i);
+        __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+        uint2 q;
+        q.x = *reinterpret_cast<uint32_t*>(&a);
+        q.y = *reinterpret_cast<uint32_t*>(&b);
+        *reinterpret_cast<uint2*>(y + i) = q;
+    }
+    if (i < n) for (long k = i; k < n && k < i + 4; ++k) y[k] = __float2bfloat16(x[k]);
+}
+
+// y[c, r] = x[r, c]  (bf16 or fp32 -> bf16), 32x32 tiles through shared memory
+template <typename TI>
+__global__ void transpose_to_bf16_kernel(const TI* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                         long rows, long cols) {
+    __shared__ float tile[32][33];
+    long c0 = (long)blockIdx.x * 32, r0 = (long)blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        long r = r0 + i, c = c0 + threadIdx.x;
+        tile[i][threadIdx.x] = (r < rows && c < cols) ? (float)x[r * cols + c] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        long c = c0 + i, r = r0 + threadIdx.x;
+        if (r < rows && c < cols) y[c * rows + r] = __float2bfloat16(tile[threadIdx.x][i]);
+    }
+}
+
+// Adam (torch.optim.Adam semantics, no amsgrad): flat fp32 bucket
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, long n, float lr, float b1, float b2, float eps,
+                            float wd, float bc1, float bc2, float gscale) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        float gi = g[i] * gscale;
+        if (wd != 0.f) gi += wd * p[i];
+        float mi = b1 * m[i] + (1.f - b1) * gi;
+        float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        float denom = sqrtf(vi) / sqrtf(bc2) + eps;
+        p[i] -= (lr / bc1) * (mi / denom);
+    }
+}
+
+__global__ void sumsq_kernel(const float* __restrict__ x, long n, float* __restrict__ out) {
+    __shared__ float sh[33];
+    float acc = 0.f;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+        acc += x[i] * x[i];
+    acc = block_sum(acc, sh);
+    if (threadIdx.x == 0) atomicAdd(out, acc);
+}
+
+inline int ew_grid(long n, int threads) {
+    long b = (n + threads - 1) / threads;
+    long cap = (long)eb_num_sms() * 32;
+    return (int)(b < 1 ? 1 : (b < cap ? b : cap));
+}
+
+}  // namespace
+
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+EB_API int eb_layernorm_fwd(const float* x, const float* res, const float* gamma, const float* beta,
+                            float* y, void* y_bf16, float* mean, float* rstd, long rows, int H,
+                            float eps, void* stream) {
+    if (!x || !gamma || !beta || !y || rows <= 0 || H <= 0 || H > 2048) return EB_ERR_INVALID;
+    long blocks = (rows + LN_WARPS - 1) / LN_WARPS;
+    long cap = (long)eb_num_sms() * 8;
+    int grid = (int)(blocks < cap ? blocks : cap);
+#define LN_FWD(PL) layernorm_fwd_kernel<PL><<<grid, LN_WARPS * 32, 0, ST(stream)>>>( \
+        x, res, gamma, beta, y, (__nv_bfloat16*)y_bf16, mean, rstd, rows, H, eps)
+    if (H <= 256) LN_FWD(8); else if (H <= 512) LN_FWD(16); else if (H <= 1024) LN_FWD(32); else LN_FWD(64);
+#undef LN_FWD
+    EB_CHECK_LAUNCH();
+    return EB_OK;
+}
+
+EB_API int eb_layernorm_bwd(const float* dy, const float* x, const float* res, const float* gamma,
+                            const float* mean, const float* rstd, float* dz, float* dgamma,
+                            float* dbeta, long rows, int H, void* stream) {
+    if (!dy || !x || !gamma || !mean || !rstd || !dz || !dgamma || !dbeta || H > 2048)
+        return EB_ERR_INVALID;
+    long blocks = (rows + LN_WARPS - 1) / LN_WARPS;
+    long cap = (long)eb_num_sms() * 8;
+    int grid = (int)(blocks < cap ? blocks : cap);
+#define LN_BWD(PL) layernorm_bwd_kernel<PL><<<grid, LN_WARPS * 32, 0, ST(stream)>>>( \
+        dy, x, res, gamma, mean, rstd, dz, rows, H)
+    if (H <= 256) LN_BWD(8); else if (H <= 512) LN_BWD(16); else if (H <= 1024) LN_BWD(32); else LN_BWD(64);
+#undef LN_BWD
+    EB_CHECK_LAUNCH();
+    long rpb = (rows + 255) / 256;
+    if (rpb < 32) rpb = 32;
+    dim3 g2((H + 127) / 128, (unsigned)((rows + rpb - 1) / rpb));
+    layernorm_param_grad_kernel<<<g2, 128, 0, ST(stream)>>>(dy, x, res, mean, rstd, dgamma, dbeta, rows, H, rpb);
+    EB_CHECK_LAUNCH();
+    return EB_OK;
+}
+
+EB_API int eb_time_reduce_fwd(const float* x, float* y, void* y_bf16, int B, int T, int H, void* stream) {
+    long n = (long)B * ((T + 1) / 2) * H;
+    time_reduce_fwd_kernel<<<ew_grid(n, 256), 256, 0, ST(stream)>>>(x, y, (__nv_bfloat16*)y_bf16, B, T, H);
+    EB_CHECK_LAUNCH();
+    return EB_OK;
+}
+EB_API int eb_time_reduce_bwd(const float* dy, float* dx, int B, int T, int H, void* stream) {
+    long n = (long)B * T * H;
+    time_reduce_bwd_kernel<<<ew_grid(n, 256), 256, 0, ST(stream)>>>(dy, dx, B, T, H);
+    EB_CHECK_LAUNCH();
+    return EB_OK;
+}
+
+EB_API int eb_embedding_fwd(const void* ids, int ids_are_int64, const float* W, float* out,
+                            void* out_bf16, int B, int U, int E, int prepend_bos, int bos, void* stream) {
+    long n = (long)B * (U + (prepend_bos ? 1 : 0)) * E;
+    if (n <= 0) return EB_OK;
+    if (ids_are_int64)
+        embedding_fwd_kernel<long long><<<ew_grid(n, 256), 256, 0, ST(stream)>>>(
+            (const long long*)ids, W, out, (__nv_bfloat16*)out_bf16, B, U, E, prepend_bos ? 1 : 0, bos);
+    else
+        embedding_fwd_kernel<int><<<ew_grid(n, 256), 256, 0, ST(stream)>>>(
+            (const int*)ids, W, out, (__nv_bfloat16*)out_bf16, B, U, E, prepend_bos ? 1 : 0, bos);
+    EB_CHECK_LAUNCH();
+    return EB_OK;
+}
+EB_API int eb_embedding_bwd(const void* ids, int ids_are_int64, const float* dout, float* dW, int B,
+                            int U, int E, int prepend_bos, int bos, int pad, void* stream) {
+    long n = (long)B * (U + (prepend_bos ? 1 : 0)) * E;
+    if (n <= 0) return EB_OK;
+    if (ids_are_int64)
+        embedding_bwd_kernel<long long><<<ew_grid(n, 256), 256, 0, ST(stream)>>>(
+            (const long long*)ids, dout, dW, B, U, E, prepend_bos ? 1 : 0, bos, pad);
+    else
+        embedding_bwd_kernel<int><<<ew_grid(n, 256), 256, 0, ST(stream)>>>(
+            (const int*)ids, dout, dW, B, U, E, prepend_bos ? 1 : 0, bos, pad);
+    EB_CHECK_LAUNCH();
+    return EB_OK;
+}
+
+EB_API int eb_joint_hidden_fwd(const float* ep, const float* dp, void* hidden, int hidden_bf16, int B,
+                               int T, int U, int J, void* stream) {
+    if (!ep || !dp || !hidden) return EB_ERR_INVALID;
+    if (hidden_bf16)
+        joint_hidden_fwd_kernel<__nv_bfloat16><<<B * T, 256, 0, ST(stream)>>>(ep, dp, (__nv_bfloat16*)hidden, B, T, U, J);
+    else
+        joint_hidden_fwd_kernel<float><<<B * T, 256, 0, ST(stream)>>>(ep, dp, (float*)hidden, B, T, U, J);
+    EB_CHECK_LAUNCH();
+    return EB_OK;
+}
+
+EB_API int eb_joint_hidden_bwd(void* dhidden_inout, const void* hidden, int is_bf16, float* dep,
+                               float* ddp, int B, int T, int U, int J, void* stream) {
+    if (!dhidden_inout || !hidden || !dep || !ddp) return EB_ERR_INVALID;
+    if (is_bf16) {
+        joint_hidden_bwd_t_kernel<__nv_bfloat16><<<B * T, 256, 0, ST(stream)>>>(
+            (__nv_bfloat16*)dhidden_inout, (const __nv_bfloat16*)hidden, dep, T, U, J);
+        joint_hidden_bwd_u_kernel<__nv_bfloat16><<<B * U, 256, 0, ST(stream)>>>(
+            (const __nv_bfloat16*)dhidden_inout, ddp, T, U, J);
+    } else {
+        joint_hidden_bwd_t_kernel<float><<<B * T, 256, 0, ST(stream)>>>(
+            (float*)dhidden_inout, (const float*)hidden, dep, T, U, J);
+        joint_hidden_bwd_u_kernel<float><<<B * U, 256, 0, ST(stream)>>>((const float*)dhidden_inout, ddp, T, U, J);
+    }
+    EB_CHECK_LAUNCH();
+    return EB_OK;
+}
+
+EB_API int eb_colsum(const void* x, int x_bf16, float* out, long rows, int N, void* stream) {
+    if (!x || !out || rows <= 0 || N <= 0) return EB_ERR_INVALID;
+    long rpb = (rows + 255) / 256;
+    if (rpb < 64) rpb = 64;
+    dim3 grid((N + 127) / 128, (unsigned)((rows + rpb - 1) / rpb));
+    if (x_bf16)
+        colsum_kernel<__nv_bfloat16><<<grid, 128, 0, ST(stream)>>>((const __nv_bfloat16*)x, out, rows, N, rpb);
+    else
+        colsum_kernel<float><<<grid, 128, 0, ST(stream)>>>((const float*)x, out, rows, N, rpb);
+    EB_CHECK_LAUNCH();
+    return EB_OK;
+}
+
+EB_API int eb_cast_bf16(const float* x, void* y, long n, void* stream) {
+    if (n <= 0) return EB_OK;
+    if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 7)) return EB_ERR_INVALID;
+    cast_bf16_kernel<<<ew_grid((n + 3) / 4, 256), 256, 0, ST(stream)>>>(x, (__nv_bfloat16*)y, n);
+    EB_CHECK_LAUNCH();
+    return EB_OK;
+}
+
+EB_API int eb_transpose_to_bf16(const void* x, int x_bf16, void* y, long rows, long cols, void* stream) {
+    dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
+    if (x_bf16)
+        transpose_to_bf16_kernel<__nv_bfloat16><<<grid, dim3(32, 8), 0, ST(stream)>>>(
+            (const __nv_bfloat16*)x, (__nv_bfloat16*)y, rows, cols);
+    else
+        transpose_to_bf16_kernel<float><<<grid, dim3(32, 8), 0, ST(stream)>>>((const float*)x, (__nv_bfloat16*)y, rows, cols);
+    EB_CHECK_LAUNCH();
+    return EB_OK;
+}
+
+EB_API int eb_adam_step(float* p, const float* g, float* m, float* v, long n, float lr, float beta1,
+                        float beta2, float eps, float weight_decay, int step, float grad_scale,
+                        void* stream) {
+    if (!p || !g || !m || !v || n <= 0 || step < 1) return EB_ERR_INVALID;
+    float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
+    adam_kernel<<<ew_grid(n, 256), 256, 0, ST(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps,
+                                                         weight_decay, bc1, bc2, grad_scale);
+    EB_CHECK_LAUNCH();
+    return EB_OK;
+}
+
+EB_API int eb_sumsq(const float* x, long n, float* out_accum, void* stream) {
+    sumsq_kernel<<<ew_grid(n, 256), 256, 0, ST(stream)>>>(x, n, out_accum);
+    EB_CHECK_LAUNCH();
+    return EB_OK;
+}

@@ -1,0 +1,303 @@
+// gemm_tc.cu -- bf16 tensor-core GEMM for sm_100a: TMA -> shared (128B swizzle) -> tcgen05.mma
+// (accumulators in TMEM) -> tcgen05.ld epilogue.  Hand-written PTX, no CUTLASS.
+//
+// Used in bf16 mode for every dense contraction of the RNN-T path:
+//   LSTM input projections  xg = X * W_ih^T          (rnnt/models.py:45-46 -> nn.LSTM)
+//   encoder/predictor projections, joint W1 halves   (rnnt/models.py:129,148,163)
+//   joint logits            logits = tanh(.) * W2^T  (rnnt/models.py:165, 2.7 TFLOP at E6D2)
+//   and their dgrad / wgrad counterparts (operands read MN-major, no transposes materialised).
+//
+// Kernel anatomy (one CTA per SM, persistent over output tiles of 128 x 128, BK = 64):
+//   warp 0      TMA producer: cp.async.bulk.tensor.2d into a 5-stage ring, mbarrier expect_tx
+//   warp 1      MMA issuer: one elected lane issues 4 x tcgen05.mma (M128 N128 K16) per stage,
+//               tcgen05.commit releases the stage / publishes the accumulator; owns TMEM alloc
+//   warps 2..5  epilogue: tcgen05.ld (32 lanes x 32 columns per warp), transpose through a padded
+//               shared tile so that global stores are 128-byte coalesced rows, + bias / + C
+//   TMEM: 2 accumulator buffers x 128 fp32 columns, so the epilogue of tile i overlaps the
+//   mainloop of tile i+1.
+#include <cuda.h>
+#include "common.cuh"
+#include "../../include/edgedict_b200.h"
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 64, STAGES = 5, UMMA_K = 16;
+constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int EPI_BYTES = 4 * 32 * 33 * 4;
+constexpr int TMEM_COLS = 256;
+constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + EPI_BYTES + 256;
+constexpr int NTHREADS = 192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    unsigned long long spins = 0;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                     " selp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (!ok && ++spins > (1ull << 26)) {   // a protocol bug must fail loudly, not hang the GPU
+            printf("[edgedict_b200] gemm_tc: mbarrier wait timeout (block %d warp %d)\n", blockIdx.x,
+                   threadIdx.x >> 5);
+            __trap();
+        }
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :: "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+                 " tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+                 :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor (sm_100 format): start>>4 | LBO>>4 @16 | SBO>>4 @32 | version 1 @46
+// | layout SWIZZLE_128B (=2) @61
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// A_MN / B_MN: operand stored with its M (resp. N) index contiguous ("MN-major"), else K contiguous.
+//   K-major tile in smem : [128 rows][64 k] bf16, 128 B per row, 128B swizzle; SBO = 1024 (8 rows)
+//   MN-major tile in smem: 2 x [64 k][64 mn] bf16, 128 B per k-row; SBO = 1024 (8 k-rows), LBO = 8192
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+               void* __restrict__ Cout, int c_bf16, const float* __restrict__ bias, int accumulate,
+               long M, int N, long K) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* tiles = smem;
+    float* epi = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + EPI_BYTES);
+    // bars: full[S], empty[S], tmem_full[2], tmem_empty[2], then tmem base pointer
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES);
+    const uint32_t tfull0 = smem_u32(bars + 2 * STAGES), tempty0 = smem_u32(bars + 2 * STAGES + 2);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long num_m = (M + BM - 1) / BM;
+    const int num_n = (N + BN - 1) / BN;
+    const long num_tiles = num_m * num_n;
+    const int nkb = (int)((K + BK - 1) / BK);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&tma_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&tma_b) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = (int)(tile / num_n) * BM, n0 = (int)(tile % num_n) * BN;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                    const uint32_t fb = full0 + 8 * stage;
+                    mbar_expect_tx(fb, STAGE_BYTES);
+                    const uint32_t sa = smem_u32(tiles + stage * STAGE_BYTES), sb = sa + A_BYTES;
+                    if (!A_MN) tma_load_2d(sa, &tma_a, kb * BK, m0, fb);
+                    else { tma_load_2d(sa, &tma_a, m0, kb * BK, fb); tma_load_2d(sa + 8192, &tma_a, m0 + 64, kb * BK, fb); }
+                    if (!B_MN) tma_load_2d(sb, &tma_b, kb * BK, n0, fb);
+                    else { tma_load_2d(sb, &tma_b, n0, kb * BK, fb); tma_load_2d(sb + 8192, &tma_b, n0 + 64, kb * BK, fb); }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // instruction descriptor: D=f32 (1<<4), A=B=bf16 (1<<7, 1<<10), majors @15/@16, N>>3 @17, M>>4 @24
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) |
+                                   ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) |
+                                   ((uint32_t)(BM >> 4) << 24);
+            int stage = 0; uint32_t phase = 0;
+            long it = 0;
+            for (long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const uint32_t acc = (uint32_t)(it & 1), acc_phase = (uint32_t)((it >> 1) & 1);
+                mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(full0 + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(tiles + stage * STAGE_BYTES), sb = sa + A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t ad = A_MN ? make_desc(sa + k * 2048, 8192, 1024) : make_desc(sa + k * 32, 0, 1024);
+                        const uint64_t bd = B_MN ? make_desc(sb + k * 2048, 8192, 1024) : make_desc(sb + k * 32, 0, 1024);
+                        tc_mma_bf16(d_tmem, ad, bd, idesc, (kb | k) ? 1u : 0u);
+                    }
+                    tc_commit(empty0 + 8 * stage);          // frees the smem stage when the MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(tfull0 + 8 * acc);                // accumulator complete -> epilogue
+            }
+        }
+    } else {
+        const int q = warp & 3;                             // TMEM lane quadrant this warp may read
+        float* buf = epi + (warp - 2) * (32 * 33);
+        long it = 0;
+        for (long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const uint32_t acc = (uint32_t)(it & 1), acc_phase = (uint32_t)((it >> 1) & 1);
+            const long m0 = (tile / num_n) * BM;
+            const int n0 = (int)(tile % num_n) * BN;
+            mbar_wait(tfull0 + 8 * acc, acc_phase);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t r[32];
+                tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c * 32, r);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) buf[lane * 33 + i] = __uint_as_float(r[i]);
+                __syncwarp();
+                const int col = n0 + c * 32 + lane;
+                const bool cok = col < N;
+                const float bv = (bias && cok) ? bias[col] : 0.f;
+#pragma unroll 4
+                for (int rr = 0; rr < 32; ++rr) {
+                    const long row = m0 + q * 32 + rr;
+                    if (row < M && cok) {
+                        float v = buf[rr * 33 + lane] + bv;
+                        if (c_bf16) {
+                            __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(Cout) + row * N + col;
+                            if (accumulate) v += __bfloat162float(*cp);
+                            *cp = __float2bfloat16(v);
+                        } else {
+                            float* cp = reinterpret_cast<float*>(Cout) + row * N + col;
+                            if (accumulate) v += *cp;
+                            *cp = v;
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            tc_fence_before();
+            if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2-D bf16 tensor [outer][inner] (inner contiguous) with a {64 x box_outer} box, 128B swizzle
+bool make_map(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer, uint32_t box_outer) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {inner * 2};
+    cuuint32_t box[2] = {64, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+template <bool A_MN, bool B_MN>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, void* C, int c_bf16, const float* bias, int accumulate,
+           long M, int N, long K, cudaStream_t st) {
+    auto kern = gemm_tc_kernel<A_MN, B_MN>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        EB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        attr_done = true;
+    }
+    const long tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    const int grid = (int)(tiles < eb_num_sms() ? tiles : eb_num_sms());
+    kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(ta, tb, C, c_bf16, bias, accumulate, M, N, K);
+    EB_CHECK_LAUNCH();
+    return EB_OK;
+}
+
+}  // namespace
+
+EB_API int eb_gemm_bf16(const void* A, int a_mn_major, const void* B, int b_mn_major, void* C, int c_bf16,
+                        const float* bias, int accumulate, long M, int N, long K, void* stream) {
+    if (!A || !B || !C || M <= 0 || N <= 0 || K <= 0) return EB_ERR_INVALID;
+    if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return EB_ERR_INVALID;
+    // contiguous dimension must keep row pitches 16-byte aligned
+    if ((a_mn_major ? M : K) % 8 || (b_mn_major ? (long)N : K) % 8) return EB_ERR_INVALID;
+    CUtensorMap ta, tb;
+    bool ok = a_mn_major ? make_map(&ta, A, (uint64_t)M, (uint64_t)K, 64) : make_map(&ta, A, (uint64_t)K, (uint64_t)M, 128);
+    ok = ok && (b_mn_major ? make_map(&tb, B, (uint64_t)N, (uint64_t)K, 64) : make_map(&tb, B, (uint64_t)K, (uint64_t)N, 128));
+    if (!ok) {
+        fprintf(stderr, "[edgedict_b200] cuTensorMapEncodeTiled failed\n");
+        return EB_ERR_CUDA;
+    }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (a_mn_major) {
+        if (b_mn_major) return launch<true, true>(ta, tb, C, c_bf16, bias, accumulate, M, N, K, st);
+        return launch<true, false>(ta, tb, C, c_bf16, bias, accumulate, M, N, K, st);
+    }
+    if (b_mn_major) return launch<false, true>(ta, tb, C, c_bf16, bias, accumulate, M, N, K, st);
+    return launch<false, false>(ta, tb, C, c_bf16, bias, accumulate, M, N, K, st);
+}

@@ -1,0 +1,263 @@
+"""Autograd glue: each Function's forward/backward is a short sequence of C-ABI calls
+(edgedict_b200/ops.py).  torch.autograd only stitches them together -- it never differentiates
+through a torch op on the hot path.
+
+Reference semantics per Function are cited next to each class (paths under /root/reference).
+"""
+import torch
+
+from . import ops
+
+f32, bf16 = torch.float32, torch.bfloat16
+
+
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+class Linear(torch.autograd.Function):
+    """nn.Linear: y = x W^T + b  (rnnt/models.py:129,148,163-167)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, precision):
+        shp = x.shape
+        x2 = _c(x).view(-1, shp[-1])
+        x16 = ops.cast_bf16(x2) if precision == "bf16" else None
+        y = ops.mm_nt(x2, w, b, precision, x16=x16)
+        ctx.save_for_backward(x2 if x16 is None else x16, w)
+        ctx.precision, ctx.has_b, ctx.shp = precision, b is not None, shp
+        return y.view(*shp[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        xs, w = ctx.saved_tensors
+        p = ctx.precision
+        dy2 = _c(dy).view(-1, dy.shape[-1])
+        dy16 = ops.cast_bf16(dy2) if p == "bf16" else None
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.mm_nn(dy2, w, p, dy16=dy16).view(ctx.shp)
+        if ctx.needs_input_grad[1]:
+            dw = ops.mm_tn(dy2, xs, p, dy16=dy16, x16=xs if p == "bf16" else None)
+        if ctx.has_b and ctx.needs_input_grad[2]:
+            db = ops.colsum(dy2)
+        return dx, dw, db, None
+
+
+class LayerNormRes(torch.autograd.Function):
+    """y = LayerNorm(x + res) (res optional): nn.LayerNorm + the residual add of
+    ResLayerNormLSTM.forward (rnnt/models.py:47,66-70,124)."""
+
+    @staticmethod
+    def forward(ctx, x, res, gamma, beta, eps):
+        x = _c(x)
+        res = _c(res) if res is not None else None
+        y, _, mean, rstd = ops.layernorm_fwd(x, res, gamma, beta, eps)
+        ctx.save_for_backward(x, res, gamma, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, res, gamma, mean, rstd = ctx.saved_tensors
+        dz, dgamma, dbeta = ops.layernorm_bwd(_c(dy), x, res, gamma, mean, rstd)
+        return dz, (dz if res is not None else None), dgamma, dbeta, None
+
+
+class TimeReduce(torch.autograd.Function):
+    """TimeReduction(2): zero-pad to even length, mean of frame pairs (rnnt/models.py:21-29)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.T = x.shape[1]
+        y, _ = ops.time_reduce_fwd(_c(x))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.time_reduce_bwd(_c(dy), ctx.T)
+
+
+class Embedding(torch.autograd.Function):
+    """nn.Embedding(padding_idx=PAD) with the optional BOS prepend of Decoder.forward
+    (rnnt/models.py:150-153)."""
+
+    @staticmethod
+    def forward(ctx, ids, w, prepend_bos, bos, pad):
+        ids = _c(ids)
+        if ids.dtype not in (torch.int32, torch.int64):
+            ids = ids.long()
+        ctx.save_for_backward(ids)
+        ctx.meta = (w.shape[0], prepend_bos, bos, pad)
+        return ops.embedding_fwd(ids, w, prepend_bos, bos)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (ids,) = ctx.saved_tensors
+        V, prepend_bos, bos, pad = ctx.meta
+        return None, ops.embedding_bwd(ids, _c(dout), V, prepend_bos, bos, pad), None, None, None
+
+
+class LSTMLayer(torch.autograd.Function):
+    """One unidirectional batch_first nn.LSTM layer (rnnt/models.py:45-46,64-65,145-147):
+    bulk input GEMM + persistent recurrent kernel; backward = BPTT kernel + three bulk GEMMs."""
+
+    @staticmethod
+    def forward(ctx, x, h0, c0, w_ih, w_hh, b_ih, b_hh, precision):
+        B, T, I = x.shape
+        H = w_hh.shape[1]
+        x2 = _c(x).view(B * T, I)
+        x16 = ops.cast_bf16(x2) if precision == "bf16" else None
+        bias = b_ih + b_hh
+        xg = ops.mm_nt(x2, w_ih, bias, precision, x16=x16).view(B, T, 4 * H)
+        h0c = _c(h0) if h0 is not None else None
+        c0c = _c(c0) if c0 is not None else None
+        need = any(ctx.needs_input_grad)     # (grad mode is off inside Function.forward)
+        y, hT, cT, gates, cseq = ops.lstm_seq_fwd(xg, _c(w_hh), h0c, c0c, need)
+        if need:
+            ctx.save_for_backward(x2 if x16 is None else x16, h0c, c0c, w_ih, w_hh, y, gates, cseq)
+            ctx.precision, ctx.dims = precision, (B, T, I, H)
+        return y, hT, cT
+
+    @staticmethod
+    def backward(ctx, dy, dhT, dcT):
+        xs, h0, c0, w_ih, w_hh, y, gates, cseq = ctx.saved_tensors
+        B, T, I, H = ctx.dims
+        p = ctx.precision
+        dy = _c(dy) if dy is not None else torch.zeros_like(y)
+        dg, dh0, dc0 = ops.lstm_seq_bwd(dy, gates, cseq, c0, _c(w_hh), _c(dhT) if dhT is not None else None,
+                                        _c(dcT) if dcT is not None else None)
+        dg2 = dg.view(B * T, 4 * H)
+        dg16 = ops.cast_bf16(dg2) if p == "bf16" else None
+        # h_{t-1} for every step: y shifted right by one frame, h0 (or zeros) in front
+        hprev = torch.empty_like(y)
+        hprev[:, 1:] = y[:, :-1]
+        if h0 is not None:
+            hprev[:, 0] = h0
+        else:
+            hprev[:, 0].zero_()
+        hp2 = hprev.view(B * T, H)
+        dx = ops.mm_nn(dg2, w_ih, p, dy16=dg16).view(B, T, I) if ctx.needs_input_grad[0] else None
+        dw_ih = ops.mm_tn(dg2, xs, p, dy16=dg16, x16=xs if p == "bf16" else None)
+        dw_hh = ops.mm_tn(dg2, hp2, p, dy16=dg16)
+        db = ops.colsum(dg2)
+        return (dx, dh0 if ctx.needs_input_grad[1] else None, dc0 if ctx.needs_input_grad[2] else None,
+                dw_ih, dw_hh, db, db.clone(), None)
+
+
+def _joint_pre(h_enc, h_dec, w1, b1, precision):
+    """ep = W1[:, :E] h_enc + b1, dp = W1[:, E:] h_dec  -- exact split of Linear(cat[e, d])."""
+    B, T, E = h_enc.shape
+    U, Dd = h_dec.shape[1], h_dec.shape[2]
+    J = w1.shape[0]
+    he2, hd2 = _c(h_enc).view(B * T, E), _c(h_dec).view(B * U, Dd)
+    ep = ops.mm_nt(he2, w1[:, :E], b1, precision).view(B, T, J)
+    dp = ops.mm_nt(hd2, w1[:, E:], None, precision).view(B, U, J)
+    return he2, hd2, ep, dp
+
+
+def _joint_bwd(ctx_p, dlog2, hid, he2, hd2, w1, w2, dims, need_w=True):
+    """Shared backward of the joint given d logits [N_cells, V] (fp32 or bf16)."""
+    B, T, U, E, Dd, J, V = dims
+    p = ctx_p
+    dl16 = dlog2 if dlog2.dtype == bf16 else (ops.cast_bf16(dlog2) if p == "bf16" else None)
+    db2 = ops.colsum(dlog2)
+    hid2 = hid.view(B * T * U, J)
+    dw2 = ops.mm_tn(dlog2, hid2, p, dy16=dl16, x16=hid2 if p == "bf16" else None)
+    dhid = ops.mm_nn(dlog2, w2, p, dy16=dl16, out_bf16=(p == "bf16"))
+    dep, ddp = ops.joint_hidden_bwd(dhid.view(B, T, U, J), hid)
+    dep2, ddp2 = dep.view(B * T, J), ddp.view(B * U, J)
+    w1e, w1d = w1[:, :E], w1[:, E:]
+    dhe = ops.mm_nn(dep2, w1e, p).view(B, T, E)
+    dhd = ops.mm_nn(ddp2, w1d, p).view(B, U, Dd)
+    dw1 = torch.empty_like(w1)
+    dw1[:, :E] = ops.mm_tn(dep2, he2, p)
+    dw1[:, E:] = ops.mm_tn(ddp2, hd2, p)
+    db1 = ops.colsum(dep2)
+    return dhe, dhd, dw1, db1, dw2, db2
+
+
+class JointLogits(torch.autograd.Function):
+    """Joint.forward on [B,T,E] x [B,U,D] -> logits [B,T,U,V] (rnnt/models.py:169-179)."""
+
+    @staticmethod
+    def forward(ctx, h_enc, h_dec, w1, b1, w2, b2, precision):
+        B, T, E = h_enc.shape
+        U, Dd = h_dec.shape[1], h_dec.shape[2]
+        J, V = w1.shape[0], w2.shape[0]
+        he2, hd2, ep, dp = _joint_pre(h_enc, h_dec, w1, b1, precision)
+        hid = ops.joint_hidden_fwd(ep, dp, precision == "bf16")
+        logits = ops.mm_nt(hid.view(B * T * U, J), w2, b2, precision, x16=hid.view(B * T * U, J) if precision == "bf16" else None)
+        ctx.save_for_backward(hid, he2, hd2, w1, w2)
+        ctx.precision, ctx.dims = precision, (B, T, U, E, Dd, J, V)
+        return logits.view(B, T, U, V)
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        hid, he2, hd2, w1, w2 = ctx.saved_tensors
+        B, T, U, E, Dd, J, V = ctx.dims
+        dl2 = _c(dlogits).view(B * T * U, V)
+        dhe, dhd, dw1, db1, dw2, db2 = _joint_bwd(ctx.precision, dl2, hid, he2, hd2, w1, w2, ctx.dims)
+        return dhe, dhd, dw1, db1, dw2, db2, None
+
+
+class RNNTLossFn(torch.autograd.Function):
+    """warprnnt_pytorch._RNNT (pytorch_binding/warprnnt_pytorch/__init__.py:10-50) on CUDA logits:
+    costs stay on the device, the gradient kernel runs in backward with the upstream gradient
+    folded in (the reference computes it eagerly and rescales it in a second pass)."""
+
+    @staticmethod
+    def forward(ctx, acts, labels, act_lens, label_lens, blank, reduction):
+        acts = _c(acts)
+        costs, ws = ops.rnnt_loss_fwd(acts, labels, act_lens, label_lens, blank, need_beta=True)
+        B = acts.shape[0]
+        ctx.save_for_backward(acts, labels, act_lens, label_lens, ws)
+        ctx.blank, ctx.reduction, ctx.B = blank, reduction, B
+        if reduction in ("sum", "mean"):
+            costs = costs.sum().unsqueeze(-1)
+            if reduction == "mean":
+                costs = costs / B
+        return costs
+
+    @staticmethod
+    def backward(ctx, go):
+        acts, labels, act_lens, label_lens, ws = ctx.saved_tensors
+        scale = 1.0 / ctx.B if ctx.reduction == "mean" else 1.0
+        g = _c(go.to(acts.dtype)).view(-1)
+        grads = ops.rnnt_loss_bwd(acts, labels, act_lens, label_lens, ctx.blank, ws, g, scale)
+        return grads, None, None, None, None, None
+
+
+class JointLoss(torch.autograd.Function):
+    """Transducer.forward's joint + loss (rnnt/models.py:234-239) as one autograd node: logits are
+    produced, consumed by the loss, and their gradient is written IN PLACE over them (fp32 mode)
+    or straight to bf16 (bf16 mode) -- no autograd copy of the 8 GB tensor is ever made."""
+
+    @staticmethod
+    def forward(ctx, h_enc, h_dec, w1, b1, w2, b2, labels, act_lens, label_lens, blank, precision):
+        B, T, E = h_enc.shape
+        U, Dd = h_dec.shape[1], h_dec.shape[2]
+        J, V = w1.shape[0], w2.shape[0]
+        he2, hd2, ep, dp = _joint_pre(h_enc, h_dec, w1, b1, precision)
+        hid = ops.joint_hidden_fwd(ep, dp, precision == "bf16")
+        hid2 = hid.view(B * T * U, J)
+        logits = ops.mm_nt(hid2, w2, b2, precision, x16=hid2 if precision == "bf16" else None).view(B, T, U, V)
+        costs, ws = ops.rnnt_loss_fwd(logits, labels, act_lens, label_lens, blank, need_beta=True)
+        ctx.save_for_backward(hid, he2, hd2, w1, w2, logits, labels, act_lens, label_lens, ws)
+        ctx.precision, ctx.dims, ctx.blank = precision, (B, T, U, E, Dd, J, V), blank
+        ctx.mark_non_differentiable(costs)
+        loss = costs.sum().unsqueeze(-1) / B
+        ctx.costs = costs
+        return loss, costs
+
+    @staticmethod
+    def backward(ctx, go, _gc):
+        hid, he2, hd2, w1, w2, logits, labels, act_lens, label_lens, ws = ctx.saved_tensors
+        B, T, U, E, Dd, J, V = ctx.dims
+        p = ctx.precision
+        g = _c(go.to(f32)).view(-1)
+        if p == "bf16":
+            dl = ops.rnnt_loss_bwd(logits, labels, act_lens, label_lens, ctx.blank, ws, g, 1.0 / B, out_bf16=True)
+        else:
+            dl = ops.rnnt_loss_bwd(logits, labels, act_lens, label_lens, ctx.blank, ws, g, 1.0 / B, out=logits)
+        dhe, dhd, dw1, db1, dw2, db2 = _joint_bwd(p, dl.view(B * T * U, V), hid, he2, hd2, w1, w2, ctx.dims)
+        return dhe, dhd, dw1, db1, dw2, db2, None, None, None, None, None

@@ -1,0 +1,316 @@
+"""Tensor-level wrappers over the C-ABI: torch supplies device memory and the current stream,
+nothing else.  Every function requires CUDA tensors and raises otherwise (no fallback)."""
+import torch
+
+from ._lib import lib
+from ._lib import check as _check
+
+
+def _s():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("edgedict_b200 ops need CUDA tensors (got a %s tensor); there is no CPU path" % t.device)
+    return t.data_ptr()
+
+
+def _need(t, dtype=None, name="tensor"):
+    if not t.is_cuda:
+        raise RuntimeError("edgedict_b200 ops need CUDA tensors (%s is on %s); there is no CPU path" % (name, t.device))
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise ValueError("%s must be contiguous" % name)
+    return t
+
+
+f32, bf16 = torch.float32, torch.bfloat16
+
+
+# ---- optional per-kernel instrumentation (bench.py) ----------------------------------------------
+class _Prof:
+    """When enabled, every wrapped C-ABI call is bracketed by CUDA events on the launching stream
+    and counted; bench.py reads `summary()` after a synchronize.  Disabled: zero overhead."""
+
+    def __init__(self):
+        self.enabled = False
+        self.events = []          # (name, start, end, bytes, flops)
+        self.launches = 0
+
+    def reset(self):
+        self.events, self.launches = [], 0
+
+    def summary(self):
+        out = {}
+        for name, a, b, nbytes, flops in self.events:
+            d = out.setdefault(name, dict(ms=0.0, calls=0, bytes=0.0, flops=0.0))
+            d["ms"] += a.elapsed_time(b)
+            d["calls"] += 1
+            d["bytes"] += nbytes
+            d["flops"] += flops
+        return out
+
+
+PROF = _Prof()
+
+
+def check(rc, what):
+    PROF.launches += 1            # every C-ABI call launches at least one of our kernels
+    _check(rc, what)
+
+
+class _timed:
+    def __init__(self, name, kernels=1, nbytes=0.0, flops=0.0):
+        self.name, self.k, self.nbytes, self.flops = name, kernels, nbytes, flops
+
+    def __enter__(self):
+        if PROF.enabled:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        PROF.launches += self.k - 1     # extra kernels beyond the one `check` counts
+        if PROF.enabled:
+            b = torch.cuda.Event(enable_timing=True)
+            b.record()
+            PROF.events.append((self.name, self.a, b, self.nbytes, self.flops))
+        return False
+
+
+def cast_bf16(x):
+    _need(x, f32, "x")
+    y = torch.empty(x.shape, dtype=bf16, device=x.device)
+    n = x.numel()
+    if n:
+        check(lib().eb_cast_bf16(_p(x), _p(y), n, _s()), "eb_cast_bf16")
+    return y
+
+
+def gemm_f32(A, sam, sak, B, sbk, sbn, M, N, K, bias=None, out=None, beta=0.0, alpha=1.0):
+    """C[M,N] = alpha*A'B' + beta*C + bias; strided views of fp32 storage (see eb_gemm_f32)."""
+    if out is None:
+        out = torch.empty(M, N, dtype=f32, device=A.device)
+    with _timed("gemm_f32", 1, 0.0, 2.0 * M * N * K):
+        check(lib().eb_gemm_f32(_p(A), sam, sak, _p(B), sbk, sbn, _p(out), N, _p(bias), M, N, K, alpha, beta, _s()),
+              "eb_gemm_f32")
+    return out
+
+
+def gemm_bf16(A, a_mn, B, b_mn, M, N, K, bias=None, out=None, out_bf16=False, accumulate=False, tag=None):
+    if out is None:
+        out = torch.empty(M, N, dtype=bf16 if out_bf16 else f32, device=A.device)
+    name = tag or ("gemm_bf16_%s%s" % ("t" if a_mn else "n", "n" if b_mn else "t"))
+    with _timed(name, 1, 2.0 * (M * K + N * K) + out.element_size() * M * N, 2.0 * M * N * K):
+        check(lib().eb_gemm_bf16(_p(A), int(a_mn), _p(B), int(b_mn), _p(out), int(out.dtype == bf16), _p(bias),
+                                 int(accumulate), M, N, K, _s()), "eb_gemm_bf16")
+    return out
+
+
+# ---- the three GEMM shapes of a Linear layer, dispatched on precision ---------------------------
+def mm_nt(x, w, bias=None, precision="fp32", x16=None, w16=None, out_bf16=False):
+    """y[M,N] = x[M,K] @ w[N,K]^T + bias.  w may be a column-slice view (fp32 mode uses strides)."""
+    M, K = x.shape
+    N = w.shape[0]
+    if precision == "bf16":
+        x16 = x16 if x16 is not None else (x if x.dtype == bf16 else cast_bf16(x))
+        w16 = w16 if w16 is not None else cast_bf16(w.contiguous())
+        return gemm_bf16(x16, 0, w16, 0, M, N, K, bias=bias, out_bf16=out_bf16)
+    _need(x, f32, "x")
+    return gemm_f32(x, K, 1, w, w.stride(1), w.stride(0), M, N, K, bias=bias)
+
+
+def mm_nn(dy, w, precision="fp32", dy16=None, w16=None, out_bf16=False):
+    """dx[M,K] = dy[M,N] @ w[N,K]."""
+    M, N = dy.shape
+    K = w.shape[1]
+    if precision == "bf16":
+        dy16 = dy16 if dy16 is not None else (dy if dy.dtype == bf16 else cast_bf16(dy))
+        w16 = w16 if w16 is not None else cast_bf16(w.contiguous())
+        return gemm_bf16(dy16, 0, w16, 1, M, K, N, out_bf16=out_bf16)
+    _need(dy, f32, "dy")
+    return gemm_f32(dy, N, 1, w, w.stride(0), w.stride(1), M, K, N)
+
+
+def mm_tn(dy, x, precision="fp32", dy16=None, x16=None, out=None, accumulate=False):
+    """dw[N,K] (+)= dy[M,N]^T @ x[M,K]  (contraction over the rows)."""
+    M, N = dy.shape
+    K = x.shape[1]
+    if precision == "bf16":
+        dy16 = dy16 if dy16 is not None else (dy if dy.dtype == bf16 else cast_bf16(dy))
+        x16 = x16 if x16 is not None else (x if x.dtype == bf16 else cast_bf16(x))
+        return gemm_bf16(dy16, 1, x16, 1, N, K, M, out=out, accumulate=accumulate)
+    _need(dy, f32, "dy")
+    _need(x, f32, "x")
+    return gemm_f32(dy, 1, N, x, K, 1, N, K, M, out=out, beta=1.0 if accumulate else 0.0)
+
+
+def colsum(x, out=None):
+    rows, N = x.shape
+    if out is None:
+        out = torch.zeros(N, dtype=f32, device=x.device)
+    check(lib().eb_colsum(_p(x), int(x.dtype == bf16), _p(out), rows, N, _s()), "eb_colsum")
+    return out
+
+
+# ---- LayerNorm / TimeReduction / Embedding -------------------------------------------------------
+def layernorm_fwd(x, res, gamma, beta, eps=1e-5, want_bf16=False):
+    H = x.shape[-1]
+    rows = x.numel() // H
+    y = torch.empty_like(x)
+    y16 = torch.empty(x.shape, dtype=bf16, device=x.device) if want_bf16 else None
+    mean = torch.empty(rows, dtype=f32, device=x.device)
+    rstd = torch.empty(rows, dtype=f32, device=x.device)
+    check(lib().eb_layernorm_fwd(_p(x), _p(res), _p(gamma), _p(beta), _p(y), _p(y16), _p(mean), _p(rstd),
+                                 rows, H, eps, _s()), "eb_layernorm_fwd")
+    return y, y16, mean, rstd
+
+
+def layernorm_bwd(dy, x, res, gamma, mean, rstd):
+    H = x.shape[-1]
+    rows = x.numel() // H
+    dz = torch.empty_like(x)
+    dgamma = torch.zeros(H, dtype=f32, device=x.device)
+    dbeta = torch.zeros(H, dtype=f32, device=x.device)
+    check(lib().eb_layernorm_bwd(_p(dy), _p(x), _p(res), _p(gamma), _p(mean), _p(rstd), _p(dz), _p(dgamma),
+                                 _p(dbeta), rows, H, _s()), "eb_layernorm_bwd")
+    return dz, dgamma, dbeta
+
+
+def time_reduce_fwd(x, want_bf16=False):
+    B, T, H = x.shape
+    y = torch.empty(B, (T + 1) // 2, H, dtype=f32, device=x.device)
+    y16 = torch.empty(y.shape, dtype=bf16, device=x.device) if want_bf16 else None
+    check(lib().eb_time_reduce_fwd(_p(x), _p(y), _p(y16), B, T, H, _s()), "eb_time_reduce_fwd")
+    return y, y16
+
+
+def time_reduce_bwd(dy, T):
+    B, _, H = dy.shape
+    dx = torch.empty(B, T, H, dtype=f32, device=dy.device)
+    check(lib().eb_time_reduce_bwd(_p(dy), _p(dx), B, T, H, _s()), "eb_time_reduce_bwd")
+    return dx
+
+
+def embedding_fwd(ids, W, prepend_bos, bos):
+    B, U = ids.shape
+    E = W.shape[1]
+    out = torch.empty(B, U + (1 if prepend_bos else 0), E, dtype=f32, device=W.device)
+    if out.numel():
+        check(lib().eb_embedding_fwd(_p(ids), int(ids.dtype == torch.int64), _p(W), _p(out), None, B, U, E,
+                                     int(prepend_bos), bos, _s()), "eb_embedding_fwd")
+    return out
+
+
+def embedding_bwd(ids, dout, V, prepend_bos, bos, pad):
+    B, U = ids.shape
+    E = dout.shape[-1]
+    dW = torch.zeros(V, E, dtype=f32, device=dout.device)
+    if dout.numel():
+        check(lib().eb_embedding_bwd(_p(ids), int(ids.dtype == torch.int64), _p(dout), _p(dW), B, U, E,
+                                     int(prepend_bos), bos, pad, _s()), "eb_embedding_bwd")
+    return dW
+
+
+# ---- LSTM recurrent part -------------------------------------------------------------------------
+_scratch = {}
+
+
+def _lstm_scratch(B, H, device):
+    key = (B, H, device)
+    t = _scratch.get(key)
+    if t is None:
+        n = lib().eb_lstm_scratch_bytes(B, H)
+        if n == 0:
+            raise ValueError("LSTM hidden size %d not supported by the persistent kernel" % H)
+        t = torch.zeros(n, dtype=torch.uint8, device=device)
+        _scratch[key] = t
+    return t
+
+
+def lstm_seq_fwd(xg, whh, h0, c0, save):
+    B, T, H4 = xg.shape
+    H = H4 // 4
+    dev = xg.device
+    y = torch.empty(B, T, H, dtype=f32, device=dev)
+    hT = torch.empty(B, H, dtype=f32, device=dev)
+    cT = torch.empty(B, H, dtype=f32, device=dev)
+    gates = torch.empty(B, T, H4, dtype=f32, device=dev) if save else None
+    cseq = torch.empty(B, T, H, dtype=f32, device=dev) if save else None
+    with _timed("lstm_seq_fwd", 1, 0.0, 2.0 * B * T * 4 * H * H):
+        check(lib().eb_lstm_seq_fwd(_p(xg), _p(whh), _p(h0), _p(c0), _p(y), _p(hT), _p(cT), _p(gates), _p(cseq),
+                                    _p(_lstm_scratch(B, H, dev)), B, T, H, _s()), "eb_lstm_seq_fwd")
+    return y, hT, cT, gates, cseq
+
+
+def lstm_seq_bwd(dy, gates, cseq, c0, whh, dhT, dcT):
+    """Returns (dgates -- written IN PLACE over `gates` --, dh0, dc0)."""
+    B, T, H = dy.shape
+    dev = dy.device
+    dh0 = torch.empty(B, H, dtype=f32, device=dev)
+    dc0 = torch.empty(B, H, dtype=f32, device=dev)
+    with _timed("lstm_seq_bwd", 1, 0.0, 2.0 * B * T * 4 * H * H):
+        check(lib().eb_lstm_seq_bwd(_p(dy), _p(gates), _p(cseq), _p(c0), _p(whh), _p(dhT), _p(dcT), _p(gates),
+                                    _p(dh0), _p(dc0), _p(_lstm_scratch(B, H, dev)), B, T, H, _s()), "eb_lstm_seq_bwd")
+    return gates, dh0, dc0
+
+
+# ---- joint + loss ----------------------------------------------------------------------------------
+def joint_hidden_fwd(ep, dp, want_bf16):
+    B, T, J = ep.shape
+    U = dp.shape[1]
+    hid = torch.empty(B, T, U, J, dtype=bf16 if want_bf16 else f32, device=ep.device)
+    check(lib().eb_joint_hidden_fwd(_p(ep), _p(dp), _p(hid), int(want_bf16), B, T, U, J, _s()), "eb_joint_hidden_fwd")
+    return hid
+
+
+def joint_hidden_bwd(dhid, hid):
+    """dhid is overwritten with d(pre-activation); returns (dep [B,T,J], ddp [B,U,J])."""
+    B, T, U, J = hid.shape
+    dep = torch.empty(B, T, J, dtype=f32, device=hid.device)
+    ddp = torch.empty(B, U, J, dtype=f32, device=hid.device)
+    check(lib().eb_joint_hidden_bwd(_p(dhid), _p(hid), int(hid.dtype == bf16), _p(dep), _p(ddp), B, T, U, J, _s()),
+          "eb_joint_hidden_bwd")
+    return dep, ddp
+
+
+def rnnt_workspace(B, T, U, dtype, device):
+    n = lib().eb_rnnt_workspace_bytes(B, T, U, 8 if dtype == torch.float64 else 4)
+    return torch.empty(n, dtype=torch.uint8, device=device)
+
+
+def rnnt_loss_fwd(logits, labels, xlen, ylen, blank, need_beta=True):
+    B, T, U, V = logits.shape
+    ds = 8 if logits.dtype == torch.float64 else 4
+    ws = rnnt_workspace(B, T, U, logits.dtype, logits.device)
+    costs = torch.empty(B, dtype=logits.dtype, device=logits.device)
+    with _timed("rnnt_loss_fwd", 3, float(ds) * B * T * U * V, 0.0):
+        check(lib().eb_rnnt_loss_fwd(_p(logits), _p(labels), _p(xlen), _p(ylen), B, T, U, V, blank, ds, _p(ws),
+                                     _p(costs), int(need_beta), _s()), "eb_rnnt_loss_fwd")
+    return costs, ws
+
+
+def rnnt_loss_bwd(logits, labels, xlen, ylen, blank, ws, gscale, host_scale, out=None, out_bf16=False):
+    B, T, U, V = logits.shape
+    ds = 8 if logits.dtype == torch.float64 else 4
+    if out is None:
+        out = torch.empty(logits.shape, dtype=bf16 if out_bf16 else logits.dtype, device=logits.device)
+    per_batch = int(gscale is not None and gscale.numel() > 1)
+    with _timed("rnnt_loss_bwd", 1, float(ds + out.element_size()) * B * T * U * V, 0.0):
+        check(lib().eb_rnnt_loss_bwd(_p(logits), _p(out), int(out.dtype == bf16), _p(labels), _p(xlen), _p(ylen), B, T,
+                                     U, V, blank, ds, _p(ws), _p(gscale), per_batch, float(host_scale), _s()),
+              "eb_rnnt_loss_bwd")
+    return out
+
+
+def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
+    check(lib().eb_adam_step(_p(p), _p(g), _p(m), _p(v), p.numel(), lr, beta1, beta2, eps, weight_decay, step,
+                             grad_scale, _s()), "eb_adam_step")
+
+
+def sumsq(x, out):
+    check(lib().eb_sumsq(_p(x), x.numel(), _p(out), _s()), "eb_sumsq")

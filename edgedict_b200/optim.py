@@ -1,0 +1,57 @@
+"""Flat-bucket optimizer state for data-parallel training ("next" row N3).
+
+All parameters of a module are re-homed into ONE contiguous fp32 buffer (``flat_params``) and
+their gradients into another (``flat_grads``): the gradient all-reduce is a single NCCL call on
+``flat_grads`` and the Adam update is a single launch of ``eb_adam_step`` over the bucket
+(replaces torch.optim.Adam in cli/baseline.py:141-156,239-245; clip_grad_norm_ via ``eb_sumsq``).
+"""
+import math
+
+import torch
+
+from . import ops
+
+
+class FlatAdam:
+    def __init__(self, module, lr=5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        params = [p for p in module.parameters() if p.requires_grad]
+        if not params:
+            raise ValueError("no parameters")
+        dev = params[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("FlatAdam needs the module on a CUDA device")
+        n = sum(p.numel() for p in params)
+        self.n = n
+        self.flat_params = torch.empty(n, dtype=torch.float32, device=dev)
+        self.flat_grads = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.m = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(n, dtype=torch.float32, device=dev)
+        off = 0
+        with torch.no_grad():
+            for p in params:
+                k = p.numel()
+                self.flat_params[off:off + k].copy_(p.reshape(-1))
+                p.data = self.flat_params[off:off + k].view(p.shape)
+                p.grad = self.flat_grads[off:off + k].view(p.shape)
+                off += k
+        self.params = params
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.step_count = 0
+        self._norm = torch.zeros(1, dtype=torch.float32, device=dev)
+
+    def zero_grad(self):
+        self.flat_grads.zero_()
+        for p in self.params:                       # autograd may have replaced .grad: re-home it
+            if p.grad is None or p.grad.data_ptr() < self.flat_grads.data_ptr() or \
+                    p.grad.data_ptr() >= self.flat_grads.data_ptr() + 4 * self.n:
+                raise RuntimeError("parameter gradient left the flat bucket")
+
+    def grad_norm(self):
+        self._norm.zero_()
+        ops.sumsq(self.flat_grads, self._norm)
+        return self._norm.sqrt()
+
+    def step(self, grad_scale=1.0, lr=None):
+        self.step_count += 1
+        ops.adam_step(self.flat_params, self.flat_grads, self.m, self.v, self.lr if lr is None else lr,
+                      self.betas[0], self.betas[1], self.eps, self.weight_decay, self.step_count, grad_scale)

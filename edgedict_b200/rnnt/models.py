@@ -1,0 +1,257 @@
+"""B200-native mirror of the reference's ``rnnt/models.py`` hot path.
+
+Same class names, constructor arguments, ``forward`` signatures, return values and
+``state_dict`` keys as /root/reference/rnnt/models.py:16-269, so ``cli/train.py``,
+``cli/baseline.py``, ``cli/lightning.py`` and ``rnnt/stream.py`` can import this module
+unchanged.  The torch ``nn.LSTM`` / ``nn.LayerNorm`` / ``nn.Linear`` / ``nn.Embedding`` objects
+below are PARAMETER CONTAINERS ONLY (identical default initialisation and checkpoint keys); their
+``forward`` is never called -- all arithmetic goes through the C-ABI of libedgedict_b200.so
+(edgedict_b200/functional.py).  CUDA tensors are mandatory: there is no CPU fallback.
+
+precision: "fp32" (default; parity mode, CUDA-core GEMMs, matches torch-CPU fp32 to ~1e-5) or
+"bf16" (tcgen05 tensor-core GEMMs with fp32 accumulation; also selected automatically inside
+``torch.autocast('cuda')``, the modern spelling of the reference's apex-O1 switch).
+"""
+import os
+
+import torch
+from torch import nn
+
+from .. import functional as Fn
+from .. import ops
+from .tokenizer import NUL, BOS, PAD
+
+_DEFAULT_PRECISION = os.environ.get("EDGEDICT_PRECISION", "fp32")
+
+
+def _precision(module):
+    if torch.is_autocast_enabled():
+        return "bf16"
+    return getattr(module, "precision", _DEFAULT_PRECISION)
+
+
+def _set_precision(root, precision):
+    assert precision in ("fp32", "bf16")
+    for m in root.modules():
+        m.precision = precision
+    return root
+
+
+class TimeReduction(nn.Module):
+    """rnnt/models.py:16-29 (only reduction_factor == 2 is used by the reference configs)."""
+
+    def __init__(self, reduction_factor=2):
+        super().__init__()
+        if reduction_factor != 2:
+            raise NotImplementedError("edgedict_b200 implements the reference's factor-2 reduction")
+        self.reduction_factor = reduction_factor
+
+    def forward(self, xs):
+        return Fn.TimeReduce.apply(xs)
+
+
+class ResLayerNormLSTM(nn.Module):
+    """rnnt/models.py:32-75.  ``lstms.{i}`` / ``projs.{i}.0`` keep the reference's key layout."""
+
+    def __init__(self, input_size, hidden_size, num_layers, dropout=0, time_reductions=[1],
+                 reduction_factor=2):
+        super().__init__()
+        self.hidden_size = hidden_size
+        self.lstms = nn.ModuleList()
+        self.projs = nn.ModuleList()
+        self.time_reductions = set(time_reductions)
+        for i in range(num_layers):
+            self.lstms.append(nn.LSTM(input_size, hidden_size, 1, batch_first=True))
+            stack = [nn.LayerNorm(hidden_size)]
+            if i in self.time_reductions:
+                stack.append(TimeReduction(reduction_factor))
+            if dropout > 0:
+                stack.append(nn.Dropout(dropout))
+            self.projs.append(nn.Sequential(*stack))
+            input_size = hidden_size
+
+    def forward(self, xs, hiddens=None):
+        p = _precision(self)
+        hs, cs = (None, None) if hiddens is None else hiddens
+        out_h, out_c = [], []
+        for i, (cell, post) in enumerate(zip(self.lstms, self.projs)):
+            h0 = None if hs is None else hs[i]
+            c0 = None if cs is None else cs[i]
+            y, hT, cT = Fn.LSTMLayer.apply(xs, h0, c0, cell.weight_ih_l0, cell.weight_hh_l0,
+                                           cell.bias_ih_l0, cell.bias_hh_l0, p)
+            ln = post[0]
+            xs = Fn.LayerNormRes.apply(y, xs if i != 0 else None, ln.weight, ln.bias, ln.eps)
+            for extra in list(post)[1:]:
+                xs = extra(xs)
+            out_h.append(hT)
+            out_c.append(cT)
+        return xs, (torch.stack(out_h, 0), torch.stack(out_c, 0))
+
+
+class Encoder(nn.Module):
+    """rnnt/models.py:119-136.  ``module`` defaults to the LSTM stack (the reference default is the
+    GRU variant, which no BASELINE config uses and which this engine does not implement)."""
+
+    def __init__(self, input_size, hidden_size, num_layers, dropout, proj_size,
+                 module=ResLayerNormLSTM, time_reductions=[1], has_proj=True):
+        super().__init__()
+        self.norm = nn.LayerNorm(input_size)
+        self.lstm = module(input_size, hidden_size, num_layers, dropout=dropout,
+                           time_reductions=time_reductions)
+        self.has_proj = has_proj
+        if has_proj:
+            self.proj = nn.Linear(hidden_size, proj_size)
+
+    def forward(self, xs, hiddens=None):
+        xs = Fn.LayerNormRes.apply(xs, None, self.norm.weight, self.norm.bias, self.norm.eps)
+        xs, hiddens = self.lstm(xs, hiddens)
+        if self.has_proj:
+            xs = Fn.Linear.apply(xs, self.proj.weight, self.proj.bias, _precision(self))
+        return xs, hiddens
+
+
+class Decoder(nn.Module):
+    """Prediction network, rnnt/models.py:139-157."""
+
+    def __init__(self, vocab_embed_size, vocab_size, hidden_size, num_layers, dropout=0,
+                 proj_size=None):
+        super().__init__()
+        self.embed = nn.Embedding(vocab_size, vocab_embed_size, padding_idx=PAD)
+        self.lstm = nn.LSTM(vocab_embed_size, hidden_size, num_layers, batch_first=True,
+                            dropout=dropout)
+        self.proj = nn.Linear(hidden_size, proj_size)
+        self.dropout = dropout
+
+    def forward(self, ys, hidden=None):
+        p = _precision(self)
+        prime = hidden is None
+        xs = Fn.Embedding.apply(ys, self.embed.weight, prime, BOS, PAD)
+        L = self.lstm.num_layers
+        hs, cs = (None, None) if prime else hidden
+        out_h, out_c = [], []
+        for k in range(L):
+            w = [getattr(self.lstm, n % k) for n in ("weight_ih_l%d", "weight_hh_l%d", "bias_ih_l%d", "bias_hh_l%d")]
+            xs, hT, cT = Fn.LSTMLayer.apply(xs, None if hs is None else hs[k], None if cs is None else cs[k],
+                                            w[0], w[1], w[2], w[3], p)
+            if self.dropout > 0 and self.training and k < L - 1:
+                xs = nn.functional.dropout(xs, self.dropout, True)      # nn.LSTM inter-layer dropout
+            out_h.append(hT)
+            out_c.append(cT)
+        ys = Fn.Linear.apply(xs, self.proj.weight, self.proj.bias, p)
+        return ys, (torch.stack(out_h, 0), torch.stack(out_c, 0))
+
+
+class Joint(nn.Module):
+    """rnnt/models.py:160-179; ``joint.0`` / ``joint.2`` key layout kept (Tanh at index 1)."""
+
+    def __init__(self, input_size, hidden_size, vocab_size):
+        super().__init__()
+        self.joint = nn.Sequential(nn.Linear(input_size, hidden_size), nn.Tanh(),
+                                   nn.Linear(hidden_size, vocab_size))
+
+    def forward(self, h_enc, h_dec):
+        two_d = h_enc.dim() == 2 and h_dec.dim() == 2
+        if two_d:
+            h_enc, h_dec = h_enc[:, None, :], h_dec[:, None, :]
+        elif not (h_enc.dim() == 3 and h_dec.dim() == 3):
+            raise AssertionError("Joint expects [B,T,E]/[B,U,D] or [B,E]/[B,D]")
+        l0, l2 = self.joint[0], self.joint[2]
+        if l0.weight.shape[1] != h_enc.shape[-1] + h_dec.shape[-1]:
+            raise ValueError("joint input size mismatch")
+        out = Fn.JointLogits.apply(h_enc, h_dec, l0.weight, l0.bias, l2.weight, l2.bias, _precision(self))
+        return out[:, 0, 0] if two_d else out
+
+
+class Transducer(nn.Module):
+    """rnnt/models.py:182-269."""
+
+    def __init__(self, vocab_embed_size, vocab_size, input_size, enc_hidden_size, enc_layers,
+                 enc_dropout, enc_proj_size, dec_hidden_size, dec_layers, dec_dropout, dec_proj_size,
+                 joint_size, enc_time_reductions=[1], blank=NUL, module_type='LSTM', output_loss=True):
+        super().__init__()
+        self.blank = blank
+        if module_type not in ['GRU', 'LSTM']:
+            raise ValueError('Unsupported module type')
+        if module_type == 'GRU':
+            raise NotImplementedError("edgedict_b200 builds the LSTM encoder (module_type='LSTM'); the GRU "
+                                      "variant (rnnt/models.py:77-116) is outside the B200 hot path")
+        self.encoder = Encoder(input_size=input_size, hidden_size=enc_hidden_size, num_layers=enc_layers,
+                               dropout=enc_dropout, proj_size=enc_proj_size,
+                               time_reductions=enc_time_reductions, module=ResLayerNormLSTM)
+        self.decoder = Decoder(vocab_embed_size=vocab_embed_size, vocab_size=vocab_size,
+                               hidden_size=dec_hidden_size, num_layers=dec_layers, dropout=dec_dropout,
+                               proj_size=dec_proj_size)
+        self.joint = Joint(input_size=enc_proj_size + dec_proj_size, hidden_size=joint_size,
+                           vocab_size=vocab_size)
+        self.output_loss = output_loss
+        if output_loss:
+            from ..warprnnt_pytorch import RNNTLoss
+            self.loss_fn = RNNTLoss(blank=blank)
+        self.last_costs = None
+
+    def set_precision(self, precision):
+        return _set_precision(self, precision)
+
+    def scale_length(self, logits, xlen):
+        return scale_length(logits.shape[1], xlen)
+
+    def forward(self, xs, ys, xlen, ylen):
+        xs = xs[:, :int(xlen.max())].contiguous()
+        ys = ys[:, :int(ylen.max())].contiguous()
+        h_enc, _ = self.encoder(xs)
+        h_dec, _ = self.decoder(ys)
+        if not self.output_loss:
+            return self.joint(h_enc, h_dec)
+        xl = scale_length(h_enc.shape[1], xlen).to(device=h_enc.device)
+        l0, l2 = self.joint.joint[0], self.joint.joint[2]
+        loss, costs = Fn.JointLoss.apply(h_enc, h_dec, l0.weight, l0.bias, l2.weight, l2.bias,
+                                         _i32(ys), _i32(xl), _i32(ylen.to(h_enc.device)), self.blank,
+                                         _precision(self))
+        self.last_costs = costs
+        return loss
+
+    @torch.no_grad()
+    def greedy_decode(self, xs, xlen):
+        """rnnt/models.py:243-269: at most one symbol per encoder frame; returns
+        (list of id arrays incl. blanks, truncated by the UNSCALED xlen as the reference does,
+        -sum log p)."""
+        h_enc, _ = self.encoder(xs)
+        B = xs.shape[0]
+        h_dec, (h_prev, c_prev) = self.decoder(torch.zeros(B, 0, dtype=torch.long, device=xs.device))
+        y_seq, log_p = [], []
+        for i in range(h_enc.shape[1]):
+            logits = self.joint(h_enc[:, i].contiguous(), h_dec[:, 0].contiguous())
+            probs = torch.log_softmax(logits, dim=1)
+            prob, pred = probs.max(dim=1)
+            y_seq.append(pred)
+            log_p.append(prob)
+            h_new, (h_next, c_next) = self.decoder(pred[:, None], (h_prev, c_prev))
+            keep = (pred != self.blank)
+            h_dec = torch.where(keep[:, None, None], h_new, h_dec)
+            h_prev = torch.where(keep[None, :, None], h_next, h_prev)
+            c_prev = torch.where(keep[None, :, None], c_next, c_prev)
+        y_seq = torch.stack(y_seq, dim=1)
+        log_p = torch.stack(log_p, dim=1).sum(dim=1)
+        out = [seq[:int(n)].cpu().numpy() for seq, n in zip(y_seq, xlen)]
+        return out, -log_p
+
+
+def _i32(t):
+    return t.to(torch.int32).contiguous()
+
+
+def scale_length(T_out, xlen):
+    """Transducer.scale_length (rnnt/models.py:223-226) on the host lengths."""
+    scale = (xlen.max().float() / T_out).ceil()
+    return (xlen / scale).ceil().int()
+
+
+def convert_lightning2normal(checkpoint):
+    """rnnt/models.py:368-380: unwrap a Lightning checkpoint; when its keys carry the ``model.``
+    prefix, drop it and re-wrap as {'model': state_dict}."""
+    if 'state_dict' not in checkpoint:
+        return checkpoint
+    sd = checkpoint['state_dict']
+    if 'model.' in next(iter(sd.keys())):
+        return {'model': {k.replace('model.', ''): v for k, v in sd.items()}}
+    return sd

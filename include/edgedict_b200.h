@@ -1,0 +1,97 @@
+/* include/edgedict_b200.h -- C ABI of libedgedict_b200.so (sm_100a).
+ *
+ * Plain pointers and sizes only; every pointer is a DEVICE pointer unless its name ends in
+ * _host; every call is asynchronous on `stream` (a cudaStream_t passed as void*) and returns
+ * 0 on success, 2 for invalid arguments, 3 for a CUDA error.  No call allocates memory:
+ * callers own all buffers (same ownership rule as warp-transducer, README.md:36-37).
+ *
+ * Each entry point names the piece of the reference it replaces (paths relative to
+ * /root/reference).  The reference has no FFI for the model path (it calls torch.nn modules),
+ * so those entry points mirror the module boundaries of rnnt/models.py.
+ */
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- RNN-T loss, device-resident costs, no host sync ------------------------------------
+ * replaces warp-transducer/include/detail/gpu_rnnt.h:82-215 (GpuRNNT::compute_cost_and_score)
+ * and warprnnt_pytorch/__init__.py:10-50 (_RNNT.forward/backward).
+ *   logits [B,maxT,maxU,V] (dtype_size 4|8), labels [B,maxU-1] int32, xlen/ylen [B] int32. */
+size_t eb_rnnt_workspace_bytes(int B, int maxT, int maxU, int dtype_size);
+int eb_rnnt_loss_fwd(const void* logits, const int* labels, const int* xlen, const int* ylen,
+                     int B, int maxT, int maxU, int V, int blank, int dtype_size,
+                     void* workspace, void* costs_dev /* [B], may be NULL */, int need_beta,
+                     void* stream);
+/* grads = d(sum_b gscale[b]*cost_b)/d logits * host_scale; grads may alias logits (in place);
+ * grads_bf16: write bf16 instead of fp32 (dtype_size 4 only). */
+int eb_rnnt_loss_bwd(const void* logits, void* grads, int grads_bf16, const int* labels,
+                     const int* xlen, const int* ylen, int B, int maxT, int maxU, int V, int blank,
+                     int dtype_size, void* workspace, const void* gscale_dev /* [1]|[B]|NULL */,
+                     int gscale_per_batch, double host_scale, void* stream);
+int eb_rnnt_workspace_views(void* workspace, int B, int maxT, int maxU, int dtype_size,
+                            void** denom, void** alphas, void** betas, void** ll_fwd, void** ll_bwd);
+
+/* ---- fp32 GEMM (parity mode of every Linear / LSTM input projection) ----------------------
+ * replaces the cuBLAS/MKL calls behind nn.Linear and nn.LSTM's input GEMM (rnnt/models.py:45-46,
+ * 129,148,163-167).  C = alpha*A'B' + beta*C + bias[n], A'(m,k)=A[m*sam+k*sak],
+ * B'(k,n)=B[k*sbk+n*sbn]. */
+int eb_gemm_f32(const float* A, long sam, long sak, const float* B, long sbk, long sbn, float* C,
+                long ldc, const float* bias, int M, int N, int K, float alpha, float beta,
+                void* stream);
+
+/* ---- bf16 tensor-core GEMM (tcgen05 + TMA + TMEM), fp32 accumulate ------------------------
+ * same call sites in bf16 mode.  A: [M,K] (a_mn_major=0, K contiguous) or [K,M] (a_mn_major=1);
+ * B: [N,K] (b_mn_major=0) or [K,N] (b_mn_major=1); C row-major [M,N] fp32 or bf16;
+ * C = A*B (+ bias[n]) (+ C when accumulate).  Pointers 16-byte aligned, contiguous dim % 8 == 0. */
+int eb_gemm_bf16(const void* A, int a_mn_major, const void* B, int b_mn_major, void* C, int c_bf16,
+                 const float* bias, int accumulate, long M, int N, long K, void* stream);
+
+/* ---- LSTM layer, recurrent part (persistent kernel) ---------------------------------------
+ * replaces the time loop of nn.LSTM (rnnt/models.py:45-46,64-65,145-147,154-155).
+ * xg [B,T,4H] = W_ih x + b_ih + b_hh (gate order i|f|g|o); whh [4H,H]; h0/c0 may be NULL (zeros).
+ * gates_save [B,T,4H] / cseq_save [B,T,H] may be NULL for inference.  scratch: zero-size-checked
+ * by eb_lstm_scratch_bytes(B,H). */
+size_t eb_lstm_scratch_bytes(int B, int H);
+int eb_lstm_seq_fwd(const float* xg, const float* whh, const float* h0, const float* c0, float* y,
+                    float* hT, float* cT, float* gates_save, float* cseq_save, void* scratch, int B,
+                    int T, int H, void* stream);
+/* BPTT: dgates [B,T,4H] (may alias gates) = d loss / d gate pre-activations; dh0/dc0 [B,H] out. */
+int eb_lstm_seq_bwd(const float* dy, const float* gates, const float* cseq, const float* c0,
+                    const float* whh, const float* dhT, const float* dcT, float* dgates, float* dh0,
+                    float* dc0, void* scratch, int B, int T, int H, void* stream);
+
+/* ---- LayerNorm(x + res) fwd/bwd, TimeReduction, Embedding -------------------------------
+ * rnnt/models.py:47,66-69,124 ; :21-29 ; :150-153.  *_bf16 outputs are optional side copies. */
+int eb_layernorm_fwd(const float* x, const float* res, const float* gamma, const float* beta, float* y,
+                     void* y_bf16, float* mean, float* rstd, long rows, int H, float eps, void* stream);
+int eb_layernorm_bwd(const float* dy, const float* x, const float* res, const float* gamma,
+                     const float* mean, const float* rstd, float* dz, float* dgamma_accum,
+                     float* dbeta_accum, long rows, int H, void* stream);
+int eb_time_reduce_fwd(const float* x, float* y, void* y_bf16, int B, int T, int H, void* stream);
+int eb_time_reduce_bwd(const float* dy, float* dx, int B, int T, int H, void* stream);
+int eb_embedding_fwd(const void* ids, int ids_are_int64, const float* W, float* out, void* out_bf16,
+                     int B, int U, int E, int prepend_bos, int bos, void* stream);
+int eb_embedding_bwd(const void* ids, int ids_are_int64, const float* dout, float* dW_accum, int B,
+                     int U, int E, int prepend_bos, int bos, int pad, void* stream);
+
+/* ---- Joint network pieces (rnnt/models.py:169-179) --------------------------------------
+ * hidden[b,t,u,:] = tanh(ep[b,t,:] + dp[b,u,:]) with ep = W1e*h_enc + b1, dp = W1d*h_dec. */
+int eb_joint_hidden_fwd(const float* ep, const float* dp, void* hidden, int hidden_bf16, int B, int T,
+                        int U, int J, void* stream);
+int eb_joint_hidden_bwd(void* dhidden_inout, const void* hidden, int is_bf16, float* dep, float* ddp,
+                        int B, int T, int U, int J, void* stream);
+
+/* ---- reductions, casts, optimizer -------------------------------------------------------- */
+int eb_colsum(const void* x, int x_bf16, float* out_accum, long rows, int N, void* stream);
+int eb_cast_bf16(const float* x, void* y, long n, void* stream);
+int eb_transpose_to_bf16(const void* x, int x_bf16, void* y, long rows, long cols, void* stream);
+int eb_adam_step(float* p, const float* g, float* m, float* v, long n, float lr, float beta1,
+                 float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
+int eb_sumsq(const float* x, long n, float* out_accum, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
