@@ -115,10 +115,11 @@ def run_ours(args):
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
+    min_warm = int(os.environ.get("EB_BENCH_MIN_WARMUP", "3"))       # only lowered for ncu captures
+    for _ in range(max(args.warmup, min_warm)):
         loss = step(xs, ys)
     barrier()
-    first_loss = float(loss)
+    first_loss = float(loss.detach())
 
     # ---- leg 1: inputs resident in HBM, per-kernel events on --------------------------------------
     sampler = ClockSampler(local)
@@ -166,6 +167,7 @@ def run_ours(args):
                           tflops=round(d["flops"] / args.steps / ms / 1e9, 2) if d["flops"] else None)
     top = max(kern, key=lambda k: kern[k]["ms_per_step"])
     hbm_kernels = ("rnnt_loss_bwd", "rnnt_loss_fwd")
+    kern = {k: v for k, v in kern.items() if v["ms_per_step"] > 0}
     if top in hbm_kernels:
         ach = kern[top]["gbs"]
         roof = dict(kernel=top, bound="hbm", achieved=ach, peak=pk["hbm"], unit="GB/s", frac=round(ach / pk["hbm"], 4))

@@ -21,6 +21,11 @@ SIGNATURES = {
     "eb_lstm_scratch_bytes": (Z, [I, I]),
     "eb_lstm_seq_fwd": (I, [P, P, P, P, P, P, P, P, P, P, I, I, I, P]),
     "eb_lstm_seq_bwd": (I, [P, P, P, P, P, P, P, P, P, P, P, I, I, I, P]),
+    "eb_lstm_tc_supported": (I, [I, I]),
+    "eb_lstm_tc_scratch_bytes": (Z, [I, I]),
+    "eb_lstm_tc_max_clusters": (I, [I]),
+    "eb_lstm_tc_fwd": (I, [P, P, P, P, P, P, P, P, P, P, P, I, I, I, P]),
+    "eb_lstm_tc_bwd": (I, [P, P, P, P, P, P, P, P, P, P, P, I, I, I, P]),
     "eb_layernorm_fwd": (I, [P, P, P, P, P, P, P, P, L, I, F, P]),
     "eb_layernorm_bwd": (I, [P, P, P, P, P, P, P, P, P, L, I, P]),
     "eb_time_reduce_fwd": (I, [P, P, P, I, I, I, P]),
@@ -29,6 +34,8 @@ SIGNATURES = {
     "eb_embedding_bwd": (I, [P, I, P, P, I, I, I, I, I, I, P]),
     "eb_joint_hidden_fwd": (I, [P, P, P, I, I, I, I, I, P]),
     "eb_joint_hidden_bwd": (I, [P, P, I, P, P, I, I, I, I, P]),
+    "eb_decode_phase_size": (I, []),
+    "eb_decode_run": (I, [P, I, P, I, P]),
     "eb_colsum": (I, [P, I, P, L, I, P]),
     "eb_cast_bf16": (I, [P, P, L, P]),
     "eb_transpose_to_bf16": (I, [P, I, P, L, L, P]),

@@ -79,6 +79,26 @@ __device__ __forceinline__ T block_sum(T v, T* sh /* >= 33 entries */) {
     return sh[32];
 }
 
+// Spin until *ctr >= target (acquire).  A protocol bug or a CTA that was never scheduled must fail
+// loudly instead of hanging the GPU: after ~4 s of spinning the kernel traps.
+__device__ __forceinline__ void spin_wait_ge(const unsigned* ctr, unsigned target) {
+    unsigned v;
+    long long t0 = 0;
+    unsigned spins = 0;
+    while (true) {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+        if (v >= target) break;
+        if ((++spins & 0xFFFF) == 0) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 8000000000LL) {
+                printf("[edgedict_b200] grid barrier timeout: block %d saw %u, wants %u\n", blockIdx.x, v, target);
+                __trap();
+            }
+        }
+    }
+}
+
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 // streaming (read-once) 128-bit load / store that do not pollute L1

@@ -339,7 +339,7 @@ inline int row_grid(long ncells, int warps) {
 template <typename T>
 int loss_fwd(const T* logits, const int* labels, const int* xlen, const int* ylen, int B, int maxT,
              int maxU, int V, int blank, void* ws, int need_beta, cudaStream_t st) {
-    if (!logits || !labels || !xlen || !ylen || !ws || B <= 0 || maxT <= 0 || maxU <= 0 || V <= 0 ||
+    if (!logits || (!labels && maxU > 1) || !xlen || !ylen || !ws || B <= 0 || maxT <= 0 || maxU <= 0 || V <= 0 ||
         blank < 0 || blank >= V || maxU > 1024)
         return EB_ERR_INVALID;
     Workspace<T> w(ws, B, maxT, maxU);
@@ -393,7 +393,7 @@ rnntStatus_t compat_entry(const T* acts, T* grads, const int* labels, const int*
                           const int* input_lengths, int V, int B, T* costs, void* workspace,
                           rnntOptions o) {
     // argument validation mirrors src/rnnt_entrypoint.cpp:49-59
-    if (!acts || !labels || !label_lengths || !input_lengths || !costs || !workspace || V <= 0 ||
+    if (!acts || (!labels && o.maxU > 1) || !label_lengths || !input_lengths || !costs || !workspace || V <= 0 ||
         B <= 0 || o.maxT <= 0 || o.maxU <= 0)
         return RNNT_STATUS_INVALID_VALUE;
     if (o.loc != RNNT_GPU) {

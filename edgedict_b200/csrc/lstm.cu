@@ -47,7 +47,7 @@ __device__ __forceinline__ void grid_arrive(unsigned* ctr) {
 }
 __device__ __forceinline__ void grid_wait(const unsigned* ctr, unsigned target) {
     if (threadIdx.x == 0) {
-        while (ld_acquire(ctr) < target) { __nanosleep(20); }
+        spin_wait_ge(ctr, target);
     }
     __syncthreads();
 }

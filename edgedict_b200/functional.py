@@ -112,10 +112,15 @@ class LSTMLayer(torch.autograd.Function):
         h0c = _c(h0) if h0 is not None else None
         c0c = _c(c0) if c0 is not None else None
         need = any(ctx.needs_input_grad)     # (grad mode is off inside Function.forward)
-        y, hT, cT, gates, cseq = ops.lstm_seq_fwd(xg, _c(w_hh), h0c, c0c, need)
+        tc = precision == "bf16" and ops.lstm_tc_supported(B, H)
+        if tc:
+            y, y16, hT, cT, gates, cseq = ops.lstm_tc_fwd(xg, ops.cast_bf16(_c(w_hh)), h0c, c0c, need)
+        else:
+            y, hT, cT, gates, cseq = ops.lstm_seq_fwd(xg, _c(w_hh), h0c, c0c, need)
+            y16 = None
         if need:
-            ctx.save_for_backward(x2 if x16 is None else x16, h0c, c0c, w_ih, w_hh, y, gates, cseq)
-            ctx.precision, ctx.dims = precision, (B, T, I, H)
+            ctx.save_for_backward(x2 if x16 is None else x16, h0c, c0c, w_ih, w_hh, y16 if tc else y, gates, cseq)
+            ctx.precision, ctx.dims, ctx.tc = precision, (B, T, I, H), tc
         return y, hT, cT
 
     @staticmethod
@@ -123,11 +128,17 @@ class LSTMLayer(torch.autograd.Function):
         xs, h0, c0, w_ih, w_hh, y, gates, cseq = ctx.saved_tensors
         B, T, I, H = ctx.dims
         p = ctx.precision
-        dy = _c(dy) if dy is not None else torch.zeros_like(y)
-        dg, dh0, dc0 = ops.lstm_seq_bwd(dy, gates, cseq, c0, _c(w_hh), _c(dhT) if dhT is not None else None,
-                                        _c(dcT) if dcT is not None else None)
-        dg2 = dg.view(B * T, 4 * H)
-        dg16 = ops.cast_bf16(dg2) if p == "bf16" else None
+        dy = _c(dy) if dy is not None else torch.zeros(B, T, H, dtype=f32, device=y.device)
+        dhT = _c(dhT) if dhT is not None else None
+        dcT = _c(dcT) if dcT is not None else None
+        if ctx.tc:
+            dg16, dh0, dc0 = ops.lstm_tc_bwd(dy, gates, cseq, c0, ops.transpose_to_bf16(_c(w_hh)), dhT, dcT)
+            dg2 = dg16.view(B * T, 4 * H)
+        else:
+            dg, dh0, dc0 = ops.lstm_seq_bwd(dy, gates, cseq, c0, _c(w_hh), dhT, dcT)
+            dg2 = dg.view(B * T, 4 * H)
+            dg16 = ops.cast_bf16(dg2) if p == "bf16" else None
+        dg16 = dg16.view(B * T, 4 * H) if dg16 is not None else None
         # h_{t-1} for every step: y shifted right by one frame, h0 (or zeros) in front
         hprev = torch.empty_like(y)
         hprev[:, 1:] = y[:, :-1]
@@ -138,7 +149,7 @@ class LSTMLayer(torch.autograd.Function):
         hp2 = hprev.view(B * T, H)
         dx = ops.mm_nn(dg2, w_ih, p, dy16=dg16).view(B, T, I) if ctx.needs_input_grad[0] else None
         dw_ih = ops.mm_tn(dg2, xs, p, dy16=dg16, x16=xs if p == "bf16" else None)
-        dw_hh = ops.mm_tn(dg2, hp2, p, dy16=dg16)
+        dw_hh = ops.mm_tn(dg2, hp2, p, dy16=dg16, x16=hp2 if hp2.dtype == bf16 else None)
         db = ops.colsum(dg2)
         return (dx, dh0 if ctx.needs_input_grad[1] else None, dc0 if ctx.needs_input_grad[2] else None,
                 dw_ih, dw_hh, db, db.clone(), None)

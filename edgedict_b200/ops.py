@@ -259,6 +259,55 @@ def lstm_seq_bwd(dy, gates, cseq, c0, whh, dhT, dcT):
     return gates, dh0, dc0
 
 
+def lstm_tc_supported(B, H):
+    return bool(lib().eb_lstm_tc_supported(B, H))
+
+
+def _lstm_tc_scratch(B, H, device):
+    key = ("tc", H, device)
+    t = _scratch.get(key)
+    if t is None:
+        t = torch.zeros(lib().eb_lstm_tc_scratch_bytes(B, H), dtype=torch.uint8, device=device)
+        _scratch[key] = t
+    return t
+
+
+def lstm_tc_fwd(xg, whh16, h0, c0, save):
+    B, T, H4 = xg.shape
+    H = H4 // 4
+    dev = xg.device
+    y = torch.empty(B, T, H, dtype=f32, device=dev)
+    y16 = torch.empty(B, T, H, dtype=bf16, device=dev)
+    hT = torch.empty(B, H, dtype=f32, device=dev)
+    cT = torch.empty(B, H, dtype=f32, device=dev)
+    gates = torch.empty(B, T, H4, dtype=f32, device=dev) if save else None
+    cseq = torch.empty(B, T, H, dtype=f32, device=dev) if save else None
+    with _timed("lstm_tc_fwd", 1, 0.0, 2.0 * B * T * 4 * H * H):
+        check(lib().eb_lstm_tc_fwd(_p(xg), _p(whh16), _p(h0), _p(c0), _p(y), _p(y16), _p(hT), _p(cT), _p(gates),
+                                   _p(cseq), _p(_lstm_tc_scratch(B, H, dev)), B, T, H, _s()), "eb_lstm_tc_fwd")
+    return y, y16, hT, cT, gates, cseq
+
+
+def lstm_tc_bwd(dy, gates, cseq, c0, whhT16, dhT, dcT):
+    B, T, H = dy.shape
+    dev = dy.device
+    dg16 = torch.empty(B, T, 4 * H, dtype=bf16, device=dev)
+    dh0 = torch.empty(B, H, dtype=f32, device=dev)
+    dc0 = torch.empty(B, H, dtype=f32, device=dev)
+    with _timed("lstm_tc_bwd", 1, 0.0, 2.0 * B * T * 4 * H * H):
+        check(lib().eb_lstm_tc_bwd(_p(dy), _p(gates), _p(cseq), _p(c0), _p(whhT16), _p(dhT), _p(dcT), _p(dg16),
+                                   _p(dh0), _p(dc0), _p(_lstm_tc_scratch(B, H, dev)), B, T, H, _s()), "eb_lstm_tc_bwd")
+    return dg16, dh0, dc0
+
+
+def transpose_to_bf16(x):
+    """x [rows, cols] (fp32 or bf16) -> bf16 [cols, rows]."""
+    rows, cols = x.shape
+    y = torch.empty(cols, rows, dtype=bf16, device=x.device)
+    check(lib().eb_transpose_to_bf16(_p(x), int(x.dtype == bf16), _p(y), rows, cols, _s()), "eb_transpose_to_bf16")
+    return y
+
+
 # ---- joint + loss ----------------------------------------------------------------------------------
 def joint_hidden_fwd(ep, dp, want_bf16):
     B, T, J = ep.shape

@@ -63,6 +63,20 @@ int eb_lstm_seq_bwd(const float* dy, const float* gates, const float* cseq, cons
                     const float* whh, const float* dhT, const float* dcT, float* dgates, float* dh0,
                     float* dc0, void* scratch, int B, int T, int H, void* stream);
 
+/* ---- LSTM layer on tensor cores (bf16 mode; H % 64 == 0, H <= 1024) ---------------------------
+ * same contract as eb_lstm_seq_fwd/bwd with bf16 recurrent operands (fp32 accumulation, fp32 cell
+ * state): whh16 [4H,H] bf16, whhT16 [H,4H] bf16 (= W_hh^T), y16 optional bf16 copy of y, dg16
+ * [B,T,4H] bf16 gate-preactivation gradients. */
+int eb_lstm_tc_supported(int B, int H);
+size_t eb_lstm_tc_scratch_bytes(int B, int H);
+int eb_lstm_tc_max_clusters(int H);   /* co-resident 8-CTA clusters of the BPTT kernel (diagnostic) */
+int eb_lstm_tc_fwd(const float* xg, const void* whh16, const float* h0, const float* c0, float* y, void* y16,
+                   float* hT, float* cT, float* gates_save, float* cseq_save, void* scratch, int B, int T,
+                   int H, void* stream);
+int eb_lstm_tc_bwd(const float* dy, const float* gates, const float* cseq, const float* c0,
+                   const void* whhT16, const float* dhT, const float* dcT, void* dg16, float* dh0, float* dc0,
+                   void* scratch, int B, int T, int H, void* stream);
+
 /* ---- LayerNorm(x + res) fwd/bwd, TimeReduction, Embedding -------------------------------
  * rnnt/models.py:47,66-69,124 ; :21-29 ; :150-153.  *_bf16 outputs are optional side copies. */
 int eb_layernorm_fwd(const float* x, const float* res, const float* gamma, const float* beta, float* y,
@@ -83,6 +97,23 @@ int eb_joint_hidden_fwd(const float* ep, const float* dp, void* hidden, int hidd
                         int U, int J, void* stream);
 int eb_joint_hidden_bwd(void* dhidden_inout, const void* hidden, int is_bf16, float* dep, float* ddp,
                         int B, int T, int U, int J, void* stream);
+
+/* ---- streaming greedy decode: one persistent kernel per audio chunk -----------------------------
+ * replaces PytorchStreamDecoder.decode's Python loop (rnnt/stream.py:93-120).  The host builds a
+ * phase program once (edgedict_b200/stream_engine.py) and launches it per chunk; see decode.cu. */
+enum { EB_PH_LN = 0, EB_PH_PAIR = 1, EB_PH_LSTM = 2, EB_PH_LINEAR = 3, EB_PH_ARGMAX = 4, EB_PH_COPY = 5 };
+typedef struct EbPhase {
+    int32_t type, S, K1, K2, N, flags, ldx1, ldx2, ldw1, ldw2, ldy, aux, aux2, hist_ld, hist_col, pad_;
+    const float *x1, *x2, *w1, *w2, *b1, *b2;
+    float *y, *y2, *c;
+    const int32_t* tok_in;
+    int32_t* tok_out;
+    int32_t* hist;
+} EbPhase;
+/* flags: 1 = tanh epilogue (LINEAR); 2 = x1 rows are embedding rows indexed by tok_in (LSTM);
+ *        4 = masked update: streams whose tok_in equals aux (blank) keep their state (LSTM). */
+int eb_decode_phase_size(void);
+int eb_decode_run(const void* phases_dev, int nphase, void* barrier_dev, int max_ctas, void* stream);
 
 /* ---- reductions, casts, optimizer -------------------------------------------------------- */
 int eb_colsum(const void* x, int x_bf16, float* out_accum, long rows, int N, void* stream);

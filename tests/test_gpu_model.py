@@ -32,7 +32,7 @@ def test_tiny_forward_matches_reference_fixture():
     assert rel_err(dh.cpu(), z["dec_h"]) < 1e-5 and rel_err(dc.cpu(), z["dec_c"]) < 1e-5
     assert rel_err(logits.cpu(), z["logits"]) < 1e-5
     out = m(xs, ys, torch.as_tensor(z["xlen"]), torch.as_tensor(z["ylen"]))
-    assert rel_err(out.cpu(), z["logits"]) < 1e-5            # output_loss=False returns logits
+    assert rel_err(out.detach().cpu(), z["logits"]) < 1e-5   # output_loss=False returns logits
 
 
 def test_tiny_loss_and_all_parameter_gradients():

@@ -186,3 +186,30 @@ def test_lstm_layer_fwd_bwd_vs_oracle(B, T, I, H):
     y2r, _, _ = mt.lstm_layer(x.double(), torch.zeros(B, H).double(), torch.zeros(B, H).double(),
                               *[t.detach() for t in ref_in[3:]])
     assert rel_err(y2.cpu(), y2r) < 1e-5
+
+
+@pytest.mark.parametrize("B,T,I,H", [(4, 6, 32, 64), (32, 9, 64, 256), (7, 5, 24, 320), (32, 4, 64, 1024), (40, 3, 16, 128)])
+def test_lstm_tensor_core_layer_vs_oracle(B, T, I, H):
+    """bf16-mode persistent LSTM (mma.sync, weights resident in registers, cluster/DSMEM reduce in
+    BPTT) vs the fp64 oracle evaluated with the SAME bf16-rounded weights.  Remaining difference:
+    h_{t-1} and dG_t are exchanged in bf16 (documented tolerance 2e-2 / 5e-2)."""
+    from edgedict_b200 import functional as Fn
+    from edgedict_b200 import ops
+    from oracle import model_torch as mt
+    assert ops.lstm_tc_supported(B, H)
+    k = 1.0 / np.sqrt(H)
+    rb = lambda t: t.bfloat16().float()
+    w_ih, w_hh = rb((torch.rand(4 * H, I) * 2 - 1) * k), rb((torch.rand(4 * H, H) * 2 - 1) * k)
+    b_ih, b_hh = (torch.rand(4 * H) * 2 - 1) * k, (torch.rand(4 * H) * 2 - 1) * k
+    x, h0, c0 = rb(_r(B, T, I, seed=1)), _r(B, H, seed=2, scale=0.5), _r(B, H, seed=3, scale=0.5)
+    dy, dh, dc = _r(B, T, H, seed=4), _r(B, H, seed=5), _r(B, H, seed=6)
+    ref_in = [t.double().requires_grad_(True) for t in (x, h0, c0, w_ih, w_hh, b_ih, b_hh)]
+    y, hT, cT = mt.lstm_layer(*ref_in, fast=False)
+    ((y * dy.double()).sum() + (hT * dh.double()).sum() + (cT * dc.double()).sum()).backward()
+    dev_in = [t.clone().cuda().requires_grad_(True) for t in (x, h0, c0, w_ih, w_hh, b_ih, b_hh)]
+    yd, hTd, cTd = Fn.LSTMLayer.apply(*dev_in, "bf16")
+    assert rel_err(yd.detach().cpu(), y.detach()) < 2e-2
+    assert rel_err(hTd.detach().cpu(), hT.detach()) < 2e-2 and rel_err(cTd.detach().cpu(), cT.detach()) < 2e-2
+    ((yd * dy.cuda()).sum() + (hTd * dh.cuda()).sum() + (cTd * dc.cuda()).sum()).backward()
+    for name, a, r in zip("x h0 c0 w_ih w_hh b_ih b_hh".split(), dev_in, ref_in):
+        assert rel_err(a.grad.cpu(), r.grad) < 5e-2, name
