@@ -23,7 +23,7 @@ SIGNATURES = {
     "eb_lstm_seq_bwd": (I, [P, P, P, P, P, P, P, P, P, P, P, I, I, I, P]),
     "eb_lstm_tc_supported": (I, [I, I]),
     "eb_lstm_tc_scratch_bytes": (Z, [I, I]),
-    "eb_lstm_tc_max_clusters": (I, [I]),
+    "eb_lstm_tc_max_clusters": (I, [I, I]),
     "eb_lstm_tc_fwd": (I, [P, P, P, P, P, P, P, P, P, P, P, I, I, I, P]),
     "eb_lstm_tc_bwd": (I, [P, P, P, P, P, P, P, P, P, P, P, I, I, I, P]),
     "eb_layernorm_fwd": (I, [P, P, P, P, P, P, P, P, L, I, F, P]),

@@ -196,56 +196,136 @@ __global__ void embedding_bwd_kernel(const I* __restrict__ ids, const float* __r
 // Joint hidden: h[b,t,u,:] = tanh(ep[b,t,:] + dp[b,u,:])   (ep already carries b1)
 // one CTA per (b,t): ep row staged in registers, loops over u; J % 4 == 0 fast path.
 // ------------------------------------------------------------------------------------------
-template <typename TO>
-__device__ __forceinline__ void store_h(TO* p, float v);
-template <> __device__ __forceinline__ void store_h<float>(float* p, float v) { *p = v; }
-template <> __device__ __forceinline__ void store_h<__nv_bfloat16>(__nv_bfloat16* p, float v) {
-    *p = __float2bfloat16(v);
+__device__ __forceinline__ float tanh_fast(float x) {     // MUFU.TANH, rel. error ~2^-11: below bf16 resolution
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
+    return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
 }
 
-template <typename TO>
-__global__ void joint_hidden_fwd_kernel(const float* __restrict__ ep, const float* __restrict__ dp,
-                                        TO* __restrict__ hid, int B, int T, int U, int J) {
+// fp32 hidden (parity mode): exact tanhf, one CTA per (b,t)
+__global__ void joint_hidden_fwd_f32_kernel(const float* __restrict__ ep, const float* __restrict__ dp,
+                                            float* __restrict__ hid, int T, int U, int J) {
     const long bt = blockIdx.x;
     const int b = (int)(bt / T);
     const float* e = ep + bt * J;
     const float* d = dp + (long)b * U * J;
-    TO* o = hid + bt * (long)U * J;
-    const int n = U * J;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        int j = i % J;
-        store_h<TO>(o + i, tanhf(e[j] + d[i]));
+    float* o = hid + bt * (long)U * J;
+    for (int i = threadIdx.x; i < U * J; i += blockDim.x) o[i] = tanhf(e[i % J] + d[i]);
+}
+
+// bf16 hidden (bench mode): each thread owns 8 consecutive j (one 16-byte store per u), e_t kept
+// in registers for the whole u loop; J % 8 == 0
+__global__ void joint_hidden_fwd_bf16_kernel(const float* __restrict__ ep, const float* __restrict__ dp,
+                                             __nv_bfloat16* __restrict__ hid, int T, int U, int J) {
+    const long bt = blockIdx.x;
+    const int b = (int)(bt / T);
+    const int J8 = J / 8;
+    for (int q = threadIdx.x; q < J8; q += blockDim.x) {
+        const float4 e0 = *reinterpret_cast<const float4*>(ep + bt * J + q * 8);
+        const float4 e1 = *reinterpret_cast<const float4*>(ep + bt * J + q * 8 + 4);
+        const float* d = dp + (long)b * U * J + q * 8;
+        __nv_bfloat16* o = hid + bt * (long)U * J + q * 8;
+#pragma unroll 4
+        for (int u = 0; u < U; ++u) {
+            const float4 d0 = *reinterpret_cast<const float4*>(d + (long)u * J);
+            const float4 d1 = *reinterpret_cast<const float4*>(d + (long)u * J + 4);
+            uint4 v;
+            v.x = pack_bf16(tanh_fast(e0.x + d0.x), tanh_fast(e0.y + d0.y));
+            v.y = pack_bf16(tanh_fast(e0.z + d0.z), tanh_fast(e0.w + d0.w));
+            v.z = pack_bf16(tanh_fast(e1.x + d1.x), tanh_fast(e1.y + d1.y));
+            v.w = pack_bf16(tanh_fast(e1.z + d1.z), tanh_fast(e1.w + d1.w));
+            *reinterpret_cast<uint4*>(o + (long)u * J) = v;
+        }
     }
 }
 
 // dpre = dh * (1 - h^2) written in place over dh; dep[b,t,:] = sum_u dpre
-template <typename TH>
-__global__ void joint_hidden_bwd_t_kernel(TH* __restrict__ dh, const TH* __restrict__ hid,
-                                          float* __restrict__ dep, int T, int U, int J) {
+__global__ void joint_hidden_bwd_t_f32_kernel(float* __restrict__ dh, const float* __restrict__ hid,
+                                              float* __restrict__ dep, int T, int U, int J) {
     const long bt = blockIdx.x;
-    TH* g = dh + bt * (long)U * J;
-    const TH* h = hid + bt * (long)U * J;
+    float* g = dh + bt * (long)U * J;
+    const float* h = hid + bt * (long)U * J;
     for (int j = threadIdx.x; j < J; j += blockDim.x) {
         float acc = 0.f;
         for (int u = 0; u < U; ++u) {
-            float hv = (float)h[(long)u * J + j];
-            float p = (float)g[(long)u * J + j] * (1.f - hv * hv);
-            g[(long)u * J + j] = (TH)p;
-            acc += p;
+            float hv = h[(long)u * J + j];
+            float pv = g[(long)u * J + j] * (1.f - hv * hv);
+            g[(long)u * J + j] = pv;
+            acc += pv;
         }
         dep[bt * J + j] = acc;
     }
 }
+__global__ void joint_hidden_bwd_t_bf16_kernel(__nv_bfloat16* __restrict__ dh, const __nv_bfloat16* __restrict__ hid,
+                                               float* __restrict__ dep, int T, int U, int J) {
+    const long bt = blockIdx.x;
+    const int J8 = J / 8;
+    for (int q = threadIdx.x; q < J8; q += blockDim.x) {
+        __nv_bfloat16* g = dh + bt * (long)U * J + q * 8;
+        const __nv_bfloat16* h = hid + bt * (long)U * J + q * 8;
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+        for (int u = 0; u < U; ++u) {
+            const uint4 hv = *reinterpret_cast<const uint4*>(h + (long)u * J);
+            uint4 gv = *reinterpret_cast<const uint4*>(g + (long)u * J);
+            const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+            uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 hf = unpack_bf16(hw[i]), gf = unpack_bf16(gw[i]);
+                const float p0 = gf.x * (1.f - hf.x * hf.x), p1 = gf.y * (1.f - hf.y * hf.y);
+                acc[2 * i] += p0;
+                acc[2 * i + 1] += p1;
+                gw[i] = pack_bf16(p0, p1);
+            }
+            *reinterpret_cast<uint4*>(g + (long)u * J) = make_uint4(gw[0], gw[1], gw[2], gw[3]);
+        }
+        float* o = dep + bt * J + q * 8;
+        *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        *reinterpret_cast<float4*>(o + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+}
 // ddp[b,u,:] = sum_t dpre[b,t,u,:]   one CTA per (b,u)
-template <typename TH>
-__global__ void joint_hidden_bwd_u_kernel(const TH* __restrict__ dpre, float* __restrict__ ddp,
-                                          int T, int U, int J) {
+__global__ void joint_hidden_bwd_u_f32_kernel(const float* __restrict__ dpre, float* __restrict__ ddp, int T,
+                                              int U, int J) {
     const int b = blockIdx.x / U, u = blockIdx.x % U;
-    const TH* g = dpre + ((long)b * T * U + u) * J;
+    const float* g = dpre + ((long)b * T * U + u) * J;
     for (int j = threadIdx.x; j < J; j += blockDim.x) {
         float acc = 0.f;
-        for (int t = 0; t < T; ++t) acc += (float)g[(long)t * U * J + j];
+        for (int t = 0; t < T; ++t) acc += g[(long)t * U * J + j];
         ddp[((long)b * U + u) * J + j] = acc;
+    }
+}
+// bf16: grid (B*U, TSPLIT): each CTA sums a T-range, one atomic per (j) at the end (ddp pre-zeroed)
+__global__ void joint_hidden_bwd_u_bf16_kernel(const __nv_bfloat16* __restrict__ dpre, float* __restrict__ ddp,
+                                               int T, int U, int J, int tchunk) {
+    const int b = blockIdx.x / U, u = blockIdx.x % U;
+    const int t0 = blockIdx.y * tchunk, t1 = min(T, t0 + tchunk);
+    const int J8 = J / 8;
+    for (int q = threadIdx.x; q < J8; q += blockDim.x) {
+        const __nv_bfloat16* g = dpre + ((long)b * T * U + u) * J + q * 8;
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+        for (int t = t0; t < t1; ++t) {
+            const uint4 gv = *reinterpret_cast<const uint4*>(g + (long)t * U * J);
+            const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 gf = unpack_bf16(gw[i]);
+                acc[2 * i] += gf.x;
+                acc[2 * i + 1] += gf.y;
+            }
+        }
+        float* o = ddp + ((long)b * U + u) * J + q * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) atomicAdd(o + i, acc[i]);
     }
 }
 
@@ -409,10 +489,12 @@ EB_API int eb_embedding_bwd(const void* ids, int ids_are_int64, const float* dou
 EB_API int eb_joint_hidden_fwd(const float* ep, const float* dp, void* hidden, int hidden_bf16, int B,
                                int T, int U, int J, void* stream) {
     if (!ep || !dp || !hidden) return EB_ERR_INVALID;
-    if (hidden_bf16)
-        joint_hidden_fwd_kernel<__nv_bfloat16><<<B * T, 256, 0, ST(stream)>>>(ep, dp, (__nv_bfloat16*)hidden, B, T, U, J);
-    else
-        joint_hidden_fwd_kernel<float><<<B * T, 256, 0, ST(stream)>>>(ep, dp, (float*)hidden, B, T, U, J);
+    if (hidden_bf16) {
+        if (J % 8) return EB_ERR_INVALID;
+        joint_hidden_fwd_bf16_kernel<<<B * T, 96, 0, ST(stream)>>>(ep, dp, (__nv_bfloat16*)hidden, T, U, J);
+    } else {
+        joint_hidden_fwd_f32_kernel<<<B * T, 256, 0, ST(stream)>>>(ep, dp, (float*)hidden, T, U, J);
+    }
     EB_CHECK_LAUNCH();
     return EB_OK;
 }
@@ -421,14 +503,22 @@ EB_API int eb_joint_hidden_bwd(void* dhidden_inout, const void* hidden, int is_b
                                float* ddp, int B, int T, int U, int J, void* stream) {
     if (!dhidden_inout || !hidden || !dep || !ddp) return EB_ERR_INVALID;
     if (is_bf16) {
-        joint_hidden_bwd_t_kernel<__nv_bfloat16><<<B * T, 256, 0, ST(stream)>>>(
+        if (J % 8) return EB_ERR_INVALID;
+        joint_hidden_bwd_t_bf16_kernel<<<B * T, 96, 0, ST(stream)>>>(
             (__nv_bfloat16*)dhidden_inout, (const __nv_bfloat16*)hidden, dep, T, U, J);
-        joint_hidden_bwd_u_kernel<__nv_bfloat16><<<B * U, 256, 0, ST(stream)>>>(
-            (const __nv_bfloat16*)dhidden_inout, ddp, T, U, J);
+        EB_CHECK_LAUNCH();
+        EB_CUDA(cudaMemsetAsync(ddp, 0, sizeof(float) * (size_t)B * U * J, ST(stream)));
+        int tsplit = (4 * eb_num_sms() + B * U - 1) / (B * U);
+        if (tsplit < 1) tsplit = 1;
+        if (tsplit > T) tsplit = T;
+        const int tchunk = (T + tsplit - 1) / tsplit;
+        joint_hidden_bwd_u_bf16_kernel<<<dim3(B * U, (T + tchunk - 1) / tchunk), 96, 0, ST(stream)>>>(
+            (const __nv_bfloat16*)dhidden_inout, ddp, T, U, J, tchunk);
     } else {
-        joint_hidden_bwd_t_kernel<float><<<B * T, 256, 0, ST(stream)>>>(
+        joint_hidden_bwd_t_f32_kernel<<<B * T, 256, 0, ST(stream)>>>(
             (float*)dhidden_inout, (const float*)hidden, dep, T, U, J);
-        joint_hidden_bwd_u_kernel<float><<<B * U, 256, 0, ST(stream)>>>((const float*)dhidden_inout, ddp, T, U, J);
+        EB_CHECK_LAUNCH();
+        joint_hidden_bwd_u_f32_kernel<<<B * U, 256, 0, ST(stream)>>>((const float*)dhidden_inout, ddp, T, U, J);
     }
     EB_CHECK_LAUNCH();
     return EB_OK;

@@ -99,7 +99,7 @@ template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                void* __restrict__ Cout, int c_bf16, const float* __restrict__ bias, int accumulate,
-               long M, int N, long K) {
+               long M, int N, long K, int ksplit) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* tiles = smem;
@@ -113,8 +113,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long num_m = (M + BM - 1) / BM;
     const int num_n = (N + BN - 1) / BN;
-    const long num_tiles = num_m * num_n;
-    const int nkb = (int)((K + BK - 1) / BK);
+    const long num_tiles = num_m * num_n * ksplit;          // work items: (output tile, K split)
+    const int nkb_total = (int)((K + BK - 1) / BK);
+    const int kb_per = (nkb_total + ksplit - 1) / ksplit;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
@@ -136,9 +137,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if (warp == 0) {
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (long wi = blockIdx.x; wi < num_tiles; wi += gridDim.x) {
+                const long tile = wi / ksplit;
+                const int kb0 = (int)(wi % ksplit) * kb_per, kb1 = min(nkb_total, kb0 + kb_per);
                 const int m0 = (int)(tile / num_n) * BM, n0 = (int)(tile % num_n) * BN;
-                for (int kb = 0; kb < nkb; ++kb) {
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(empty0 + 8 * stage, phase ^ 1);
                     const uint32_t fb = full0 + 8 * stage;
                     mbar_expect_tx(fb, STAGE_BYTES);
@@ -159,12 +162,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                                    ((uint32_t)(BM >> 4) << 24);
             int stage = 0; uint32_t phase = 0;
             long it = 0;
-            for (long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            for (long wi = blockIdx.x; wi < num_tiles; wi += gridDim.x, ++it) {
+                const int kb0 = (int)(wi % ksplit) * kb_per, kb1 = min(nkb_total, kb0 + kb_per);
                 const uint32_t acc = (uint32_t)(it & 1), acc_phase = (uint32_t)((it >> 1) & 1);
                 mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int kb = 0; kb < nkb; ++kb) {
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(full0 + 8 * stage, phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(tiles + stage * STAGE_BYTES), sb = sa + A_BYTES;
@@ -172,7 +176,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         const uint64_t ad = A_MN ? make_desc(sa + k * 2048, 8192, 1024) : make_desc(sa + k * 32, 0, 1024);
                         const uint64_t bd = B_MN ? make_desc(sb + k * 2048, 8192, 1024) : make_desc(sb + k * 32, 0, 1024);
-                        tc_mma_bf16(d_tmem, ad, bd, idesc, (kb | k) ? 1u : 0u);
+                        tc_mma_bf16(d_tmem, ad, bd, idesc, ((kb - kb0) | k) ? 1u : 0u);
                     }
                     tc_commit(empty0 + 8 * stage);          // frees the smem stage when the MMAs retire
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -184,7 +188,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const int q = warp & 3;                             // TMEM lane quadrant this warp may read
         float* buf = epi + (warp - 2) * (32 * 33);
         long it = 0;
-        for (long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        for (long wi = blockIdx.x; wi < num_tiles; wi += gridDim.x, ++it) {
+            const long tile = wi / ksplit;
+            const int ks = (int)(wi % ksplit);
+            const bool empty_split = ks * kb_per >= nkb_total;      // (only when K is tiny) nothing accumulated
             const uint32_t acc = (uint32_t)(it & 1), acc_phase = (uint32_t)((it >> 1) & 1);
             const long m0 = (tile / num_n) * BM;
             const int n0 = (int)(tile % num_n) * BN;
@@ -199,13 +206,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 __syncwarp();
                 const int col = n0 + c * 32 + lane;
                 const bool cok = col < N;
-                const float bv = (bias && cok) ? bias[col] : 0.f;
+                const float bv = (bias && cok && ks == 0) ? bias[col] : 0.f;
 #pragma unroll 4
                 for (int rr = 0; rr < 32; ++rr) {
                     const long row = m0 + q * 32 + rr;
                     if (row < M && cok) {
-                        float v = buf[rr * 33 + lane] + bv;
-                        if (c_bf16) {
+                        float v = (empty_split ? 0.f : buf[rr * 33 + lane]) + bv;
+                        if (ksplit > 1) {
+                            atomicAdd(reinterpret_cast<float*>(Cout) + row * N + col, v);   // fp32 C, pre-zeroed / accumulate
+                        } else if (c_bf16) {
                             __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(Cout) + row * N + col;
                             if (accumulate) v += __bfloat162float(*cp);
                             *cp = __float2bfloat16(v);
@@ -265,15 +274,27 @@ bool make_map(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer,
 template <bool A_MN, bool B_MN>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, void* C, int c_bf16, const float* bias, int accumulate,
            long M, int N, long K, cudaStream_t st) {
+    const long out_tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    const long nkb = (K + BK - 1) / BK;
+    // split-K (weight gradients: few output tiles, contraction over millions of rows): fill the
+    // machine ~2x over, keep >= 16 k-blocks per split; partial tiles are reduced with fp32 atomics
+    int ksplit = 1;
+    if (!c_bf16 && out_tiles < eb_num_sms() && nkb >= 64) {
+        long want = (2L * eb_num_sms() + out_tiles - 1) / out_tiles;
+        long cap = nkb / 16;
+        ksplit = (int)(want < cap ? want : cap);
+        if (ksplit < 1) ksplit = 1;
+    }
+    if (ksplit > 1 && !accumulate) EB_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, st));
     auto kern = gemm_tc_kernel<A_MN, B_MN>;
     static bool attr_done = false;
     if (!attr_done) {
         EB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr_done = true;
     }
-    const long tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    const long tiles = out_tiles * ksplit;
     const int grid = (int)(tiles < eb_num_sms() ? tiles : eb_num_sms());
-    kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(ta, tb, C, c_bf16, bias, accumulate, M, N, K);
+    kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(ta, tb, C, c_bf16, bias, accumulate, M, N, K, ksplit);
     EB_CHECK_LAUNCH();
     return EB_OK;
 }

@@ -9,15 +9,21 @@
 //     owns a K-range of H/8 columns (<= 8 k-steps x 2 m-tiles x 4 regs = 64 registers);
 //   * h_{t-1} (bf16, [batch][H]) is exchanged through an L2-resident double buffer; each warp
 //     pulls only its own K-range with cp.async and feeds ldmatrix B-fragments; the 8 partial
-//     accumulators are summed through shared memory; one grid barrier per timestep.
-// Backward (BPTT): 2-D decomposition, cluster of 8 CTAs per 64-unit slice: CTA (js, rs) holds
-//   W_hh[rs-th eighth of the 4H gate rows, 64 units of slice js] as A-fragments, multiplies by its
-//   K-slice of dG_t (bf16 exchange buffer), reduces across warps in shared memory and across the
-//   cluster through distributed shared memory, then the owning threads run the gate-gradient
-//   math for step t-1 with dh/dc carried in registers.
+//     accumulators are summed through shared memory; one grid barrier per timestep whose
+//     release (one 16-byte store per batch row + ONE thread's fence + atomic) is issued before
+//     the non-critical stores (y, saved gates, cell states) so that they overlap the wait.
+// Backward (BPTT): 2-D decomposition: a group of CS CTAs owns 8*CS hidden units and splits the 4H
+//   gate rows (the contraction) CS ways; W_hh^T A-fragments in registers (64 regs for any CS at
+//   H=1024); partial [8*CS units x batch] tiles are reduce-scattered
+//     CLUSTER = true : across a thread-block cluster through DISTRIBUTED SHARED MEMORY behind one
+//                      hardware cluster barrier (CS = 8, 4 or 2, the largest that is co-resident);
+//     CLUSTER = false: through L2 behind a per-group software barrier (always launchable);
+//   the owning threads then run the gate-gradient math for step t-1 (inputs prefetched during the
+//   wait) with dh/dc carried in registers, and publish dG_t in bf16.
 //
 // Semantics: nn.LSTM cell, gate order i|f|g|o (rnnt/models.py:45-46 -> torch.nn.LSTM).
 #include <cooperative_groups.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "../../include/edgedict_b200.h"
 
@@ -26,9 +32,10 @@ namespace cg = cooperative_groups;
 namespace {
 
 constexpr int NW = 8;            // warps per CTA
-constexpr int UPC = 8;           // hidden units per CTA (forward)
+constexpr int UPC = 8;           // hidden units finalised per CTA
 constexpr int PAD = 8;           // bf16 elements of row padding (16 B) -> conflict-free ldmatrix
 constexpr int NB = 32;           // batch tile
+constexpr size_t TC_HDR = 2048;  // scratch: [0,1024) grid barrier counter, [1024,2048) per-group barriers
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -36,11 +43,6 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 }
 __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
-}
-__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
 }
 __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_row) {
     unsigned a = (unsigned)__cvta_generic_to_shared(smem_row);
@@ -55,12 +57,70 @@ __device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], 
 __device__ __forceinline__ uint32_t ldg_u32(const __nv_bfloat16* p) {
     return *reinterpret_cast<const uint32_t*>(p);
 }
-// every warp's lane 0 polls; no block-wide barrier on the wait side
-__device__ __forceinline__ void warp_wait(const unsigned* ctr, unsigned target) {
-    if ((threadIdx.x & 31) == 0) {
-        spin_wait_ge(ctr, target);
+// bf16-mode gate nonlinearities: ex2.approx + rcp.approx (abs. error ~1e-7, far below the bf16
+// rounding of the exchanged h); the fp32 parity kernels in lstm.cu keep expf/tanhf.
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); }
+
+// one warp copies its K-range (cpr 16-byte chunks per row, NB rows) of the exchange buffer into a
+// padded shared tile.  No integer division in the common case (cpr divides 32).
+__device__ __forceinline__ void warp_pull(__nv_bfloat16* dst, int dst_ld, const __nv_bfloat16* src, int src_ld,
+                                          int cpr) {
+    const int l = threadIdx.x & 31;
+    if (cpr > 0 && (32 % cpr) == 0) {
+        const int rstep = 32 / cpr;
+        int r = l / cpr;
+        const int q = l % cpr;
+        __nv_bfloat16* d = dst + (size_t)r * dst_ld + q * 8;
+        const __nv_bfloat16* g = src + (size_t)r * src_ld + q * 8;
+        for (; r < NB; r += rstep) {
+            cp_async16(d, g);
+            d += (size_t)rstep * dst_ld;
+            g += (size_t)rstep * src_ld;
+        }
+    } else {
+        for (int i = l; i < NB * cpr; i += 32) {
+            const int r = i / cpr, q = i % cpr;
+            cp_async16(dst + (size_t)r * dst_ld + q * 8, src + (size_t)r * src_ld + q * 8);
+        }
     }
+    cp_async_wait_all();
     __syncwarp();
+}
+
+// ---- dataflow synchronisation: ONE FLAG PER PRODUCER CTA, no atomics -----------------------------
+// A CTA publishes its slice of the exchange buffer and then stores its own monotonically increasing
+// flag with release semantics; a consumer warp needs only the producers of its own K-range, and
+// polls their (contiguous) flags with one lane per producer -- one coalesced request per poll.
+__device__ __forceinline__ void flag_release(unsigned* flag, unsigned value) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(flag), "r"(value) : "memory");
+}
+// lanes [0, n) each wait until flags[first + lane] >= target (n <= 32)
+__device__ __forceinline__ void flags_wait(const unsigned* flags, int first, int n, unsigned target) {
+    const int l = threadIdx.x & 31;
+    if (l < n) spin_wait_ge(flags + first + l, target);
+    __syncwarp();
+}
+// legacy counter barrier (per-group reduce of the non-cluster BPTT variant)
+__device__ __forceinline__ void warp_wait(const unsigned* ctr, unsigned target) {
+    if ((threadIdx.x & 31) == 0) spin_wait_ge(ctr, target);
+    __syncwarp();
+}
+__device__ __forceinline__ void warp_release(unsigned* ctr) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) {
+        __threadfence();
+        atomicAdd(ctr, 1u);
+    }
+}
+// B fragments for one k-step and all four batch n-tiles out of a padded [NB][ld] bf16 tile
+__device__ __forceinline__ void load_b(uint32_t (&b01)[4], uint32_t (&b23)[4], const __nv_bfloat16* tile, int ld,
+                                       int kstep) {
+    const int l = threadIdx.x & 31;
+    const int mrow = (l & 7) + ((l >> 4) & 1) * 8;
+    const int mk = kstep * 16 + ((l >> 3) & 1) * 8;
+    ldmatrix_x4(b01, tile + (size_t)mrow * ld + mk);
+    ldmatrix_x4(b23, tile + (size_t)(16 + mrow) * ld + mk);
 }
 
 struct FwdP {
@@ -71,6 +131,8 @@ struct FwdP {
     __nv_bfloat16* hx;            // [2][NB][H] exchange
     unsigned* bar;
     int B, T, H;
+    int dbg;                      // timing experiments only (EDGEDICT_TC_DBG): 1 skip wait, 2 skip pull+mma,
+                                  // 4 skip non-critical stores, 8 single poller, 16 skip fence
 };
 
 __global__ void __launch_bounds__(NW * 32, 1) lstm_tc_fwd_kernel(FwdP p) {
@@ -79,15 +141,17 @@ __global__ void __launch_bounds__(NW * 32, 1) lstm_tc_fwd_kernel(FwdP p) {
     const int HP = H + PAD;
     __nv_bfloat16* hs = reinterpret_cast<__nv_bfloat16*>(smraw);                 // [NB][HP]
     float* red = reinterpret_cast<float*>(smraw + (size_t)NB * HP * 2);          // [NW][32][32]
+    __nv_bfloat16* sh_h = reinterpret_cast<__nv_bfloat16*>(red + NW * 32 * 32);  // [NB][UPC]
     const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
     const int j0 = blockIdx.x * UPC;
     const unsigned ncta = gridDim.x;
-    const int nks = H / 16;                                  // k-steps in total
-    const int ksper = (nks + NW - 1) / NW;                   // per warp (<= 8)
+    const int nks = H / 16;
+    const int ksper = (nks + NW - 1) / NW;                   // <= 8
     const int ks0 = w * ksper;
     const int myks = max(0, min(ksper, nks - ks0));
+    const size_t xstride = (size_t)NB * H;
 
-    // ---- resident A fragments: afr[mt][ks][4]; mt 0 = rows (i: 0-7, f: 8-15), mt 1 = (g, o)
+    // resident A fragments: afr[mt][ks][4]; mt 0 = rows (i: 0-7, f: 8-15), mt 1 = (g, o)
     uint32_t afr[2][8][4];
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
@@ -104,38 +168,41 @@ __global__ void __launch_bounds__(NW * 32, 1) lstm_tc_fwd_kernel(FwdP p) {
             afr[mt][ks][3] = ok ? ldg_u32(rhi + 8) : 0u;
         }
 
-    // ---- the (unit, batch) pair this thread finalises every step
+    // the (unit, batch) pair this thread finalises every step
     const int ju = l >> 2;
     const int bb = (w >> 1) * 8 + (l & 3) * 2 + (w & 1);
     const int j = j0 + ju;
     const bool own = bb < B;
     float c_state = (own && p.c0) ? p.c0[(long)bb * H + j] : 0.f;
-    __nv_bfloat16* hx[2] = {p.hx, p.hx + (size_t)NB * H};
-    if (own) hx[1][(long)bb * H + j] = __float2bfloat16(p.h0 ? p.h0[(long)bb * H + j] : 0.f);
-    __threadfence();
+    if (own) p.hx[xstride + (long)bb * H + j] = __float2bfloat16(p.h0 ? p.h0[(long)bb * H + j] : 0.f);
     __syncthreads();
-    if (tid == 0) atomicAdd(p.bar, 1u);
+    if (tid == 0) { __threadfence(); atomicAdd(p.bar, 1u); }
     unsigned epoch = 1;
 
+    // running pointers of this thread's (batch row, unit) element: advance by one frame per step
+    const float* xg_p = p.xg + (long)bb * T * 4 * H + j;
+    float* y_p = p.y + (long)bb * T * H + j;
+    __nv_bfloat16* y16_p = p.y16 ? p.y16 + (long)bb * T * H + j : nullptr;
+    float* g_p = p.gates ? p.gates + (long)bb * T * 4 * H + j : nullptr;
+    float* c_p = p.cseq ? p.cseq + (long)bb * T * H + j : nullptr;
     float px[4];
 #pragma unroll
-    for (int g = 0; g < 4; ++g) px[g] = own ? __ldg(p.xg + ((long)bb * T + 0) * 4 * H + (long)g * H + j) : 0.f;
+    for (int g = 0; g < 4; ++g) px[g] = own ? __ldg(xg_p + (long)g * H) : 0.f;
 
     for (int t = 0; t < T; ++t) {
-        const __nv_bfloat16* hprev = hx[(t + 1) & 1];
-        __nv_bfloat16* hnext = hx[t & 1];
-        warp_wait(p.bar, epoch * ncta);
-        // pull this warp's K-range of h_{t-1}: NB rows x (myks*16) bf16
-        {
-            const int chunks_per_row = myks * 2;                 // 16-byte chunks
-            const int kbase = ks0 * 16;
-            for (int i = l; i < NB * chunks_per_row; i += 32) {
-                const int r = i / chunks_per_row, q = i % chunks_per_row;
-                cp_async16(hs + (size_t)r * HP + kbase + q * 8, hprev + (size_t)r * H + kbase + q * 8);
+        const __nv_bfloat16* hprev = p.hx + ((t + 1) & 1) * xstride;
+        __nv_bfloat16* hnext = p.hx + (t & 1) * xstride;
+        if (!(p.dbg & 1)) {
+            // grid barrier, wait side: ONE poller per CTA (8 pollers per CTA cost ~1.1 us/step of L2
+            // contention on the counter line), then a block barrier
+            if (tid == 0) {
+                if (p.dbg & 1024) { const volatile unsigned* f = p.bar; while (*f < epoch * ncta) {} }
+                else spin_wait_ge(p.bar, epoch * ncta);
             }
-            cp_async_wait_all();
-            __syncwarp();
+            __syncthreads();
         }
+        // pull this warp's K-range of h_{t-1}: NB rows x (myks*16) bf16
+        if (!(p.dbg & 2)) warp_pull(hs + ks0 * 16, HP, hprev + ks0 * 16, H, myks * 2);
         float acc[2][4][4];
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
@@ -145,13 +212,9 @@ __global__ void __launch_bounds__(NW * 32, 1) lstm_tc_fwd_kernel(FwdP p) {
                 for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
-            if (ks < myks) {
+            if (ks < myks && !(p.dbg & 2)) {
                 uint32_t b01[4], b23[4];
-                // lanes 0-7 / 8-15 / 16-23 / 24-31 address matrices (nt, k-lo), (nt, k-hi), (nt+1, k-lo), (nt+1, k-hi)
-                const int mrow = (l & 7) + ((l >> 4) & 1) * 8;
-                const int mk = (ks0 + ks) * 16 + ((l >> 3) & 1) * 8;
-                ldmatrix_x4(b01, hs + (size_t)mrow * HP + mk);
-                ldmatrix_x4(b23, hs + (size_t)(16 + mrow) * HP + mk);
+                load_b(b01, b23, hs, HP, ks0 + ks);
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt) {
                     mma_bf16(acc[mt][0], afr[mt][ks], b01[0], b01[1]);
@@ -169,8 +232,8 @@ __global__ void __launch_bounds__(NW * 32, 1) lstm_tc_fwd_kernel(FwdP p) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) red[(w * 32 + nt * 8 + mt * 4 + i) * 32 + l] = acc[mt][nt][i];
         __syncthreads();
-        {
-            // this thread: nt = w>>1, batch offset = w&1 -> slots (i: mt0,c=off) (f: mt0,c=2+off) (g: mt1,off) (o: mt1,2+off)
+        float ig = 0.f, fg = 0.f, gg = 0.f, og = 0.f, hn = 0.f;
+        {   // nt = w>>1, batch offset = w&1 -> slots (i: mt0,c=off) (f: mt0,c=2+off) (g: mt1,off) (o: mt1,2+off)
             const int nt = w >> 1, off = w & 1;
             float s[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -181,33 +244,41 @@ __global__ void __launch_bounds__(NW * 32, 1) lstm_tc_fwd_kernel(FwdP p) {
                 s[2] += r[(4 + off) * 32];
                 s[3] += r[(6 + off) * 32];
             }
-            if (own) {
-                const float ig = sigmoidf_(s[0] + px[0]);
-                const float fg = sigmoidf_(s[1] + px[1]);
-                const float gg = tanhf(s[2] + px[2]);
-                const float og = sigmoidf_(s[3] + px[3]);
-                c_state = fg * c_state + ig * gg;
-                const float hn = og * tanhf(c_state);
-                const long bt = (long)bb * T + t;
-                hnext[(long)bb * H + j] = __float2bfloat16(hn);
-                p.y[bt * H + j] = hn;
-                if (p.y16) p.y16[bt * H + j] = __float2bfloat16(hn);
-                if (p.gates) {
-                    float* gp = p.gates + bt * 4 * H + j;
-                    gp[0] = ig; gp[H] = fg; gp[2 * (long)H] = gg; gp[3 * (long)H] = og;
-                }
-                if (p.cseq) p.cseq[bt * H + j] = c_state;
-                if (t == T - 1) { p.hT[(long)bb * H + j] = hn; p.cT[(long)bb * H + j] = c_state; }
+            ig = fast_sigmoid(s[0] + px[0]);
+            fg = fast_sigmoid(s[1] + px[1]);
+            gg = fast_tanh(s[2] + px[2]);
+            og = fast_sigmoid(s[3] + px[3]);
+            c_state = fg * c_state + ig * gg;
+            hn = og * fast_tanh(c_state);
+            sh_h[bb * UPC + ju] = __float2bfloat16(own ? hn : 0.f);
+        }
+        __syncthreads();
+        if (w == 0) {   // publish h_t: one 16-byte store per batch row, then a single fence + arrive
+            *reinterpret_cast<uint4*>(hnext + (size_t)l * H + j0) = *reinterpret_cast<const uint4*>(sh_h + l * UPC);
+            __syncwarp();
+            if (l == 0) {
+                if (p.dbg & 16) atomicAdd(p.bar, 1u);                                   // (unsafe reference point)
+                else if (p.dbg & 256) { asm volatile("fence.acq_rel.gpu;" ::: "memory"); atomicAdd(p.bar, 1u); }
+                else if (p.dbg & 512) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(p.bar) : "memory");
+                else { __threadfence(); atomicAdd(p.bar, 1u); }
             }
         }
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) atomicAdd(p.bar, 1u);
         ++epoch;
+        // everything below overlaps the other CTAs' progress towards the barrier
+        if (own && !(p.dbg & 4)) {
+            *y_p = hn;
+            if (y16_p) *y16_p = __float2bfloat16(hn);
+            if (g_p) { g_p[0] = ig; g_p[H] = fg; g_p[2 * (long)H] = gg; g_p[3 * (long)H] = og; }
+            if (c_p) *c_p = c_state;
+            if (t == T - 1) { p.hT[(long)bb * H + j] = hn; p.cT[(long)bb * H + j] = c_state; }
+        }
+        y_p += H; xg_p += 4 * (long)H;
+        if (y16_p) y16_p += H;
+        if (g_p) g_p += 4 * (long)H;
+        if (c_p) c_p += H;
         if (t + 1 < T) {
 #pragma unroll
-            for (int g = 0; g < 4; ++g)
-                px[g] = own ? __ldg(p.xg + ((long)bb * T + t + 1) * 4 * H + (long)g * H + j) : 0.f;
+            for (int g = 0; g < 4; ++g) px[g] = own ? __ldg(xg_p + (long)g * H) : 0.f;
         }
     }
 }
@@ -221,117 +292,137 @@ struct BwdP {
     float* dh0; float* dc0;
     __nv_bfloat16* gx;            // [2][NB][4H] exchange
     unsigned* bar;
-    unsigned* gbar;               // per 64-unit slice counters (non-cluster variant)
-    float* pglob;                 // [H/64][8][JS][NB] partial tiles in L2 (non-cluster variant)
+    unsigned* gbar;               // per-group counters (non-cluster variant)
+    float* pglob;                 // [H/(8*CS)][CS][8*CS][NB] partial tiles in L2 (non-cluster variant)
     int B, T, H;
 };
 
-constexpr int JS = 64;           // units per cluster (j-slice); 8 CTAs of a cluster split the 4H rows
-
-// CLUSTER = true : the 8 CTAs of a 64-unit slice form a thread-block cluster; partial tiles are
-//                  exchanged through distributed shared memory behind one hardware cluster barrier.
-// CLUSTER = false: same decomposition on a plain cooperative grid; partial tiles go through L2 and
-//                  a per-slice software barrier (used when 16 clusters of 8 cannot be co-resident).
-template <bool CLUSTER>
+template <int CS, bool CLUSTER>
 __global__ void __launch_bounds__(NW * 32, 1) lstm_tc_bwd_kernel(BwdP p) {
+    constexpr int MT = CS / 2;                               // m16 tiles: 8*CS units
+    constexpr int JS = 8 * CS;                               // units per group
+    constexpr int KSMAX = 32 / CS;                           // k-steps per warp at H = 1024
+    constexpr int SLOTS = MT * 16;                           // accumulator registers per thread
     extern __shared__ __align__(16) unsigned char smraw[];
     const int H = p.H, B = p.B, T = p.T, H4 = 4 * H;
-    const int KR = H4 / 8;                                   // gate rows (contraction) per CTA = H/2
+    const int KR = H4 / CS;                                  // gate rows (contraction) per CTA
     const int KP = KR + PAD;
     __nv_bfloat16* gs = reinterpret_cast<__nv_bfloat16*>(smraw);                 // [NB][KP]
-    float* red = reinterpret_cast<float*>(smraw + (size_t)NB * KP * 2);          // [NW][64][32]
-    float* part = red + NW * 64 * 32;                                            // [JS][NB]
+    float* red = reinterpret_cast<float*>(smraw + (size_t)NB * KP * 2);          // [NW][SLOTS][32]
+    float* part = red + NW * SLOTS * 32;                                         // [2][JS][NB] (step parity)
+    __nv_bfloat16* sg = reinterpret_cast<__nv_bfloat16*>(part + 2 * JS * NB);    // [NB][4][UPC]  (gate-major, for dg16)
+    __nv_bfloat16* sx = sg + NB * 4 * UPC;                                       // [NB][UPC][4]  (unit-major, exchange)
     const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
-    const int rs = blockIdx.x & 7;                           // which eighth of the 4H rows (= cluster rank)
-    const int js = blockIdx.x >> 3;                          // which 64-unit slice
+    const int rs = blockIdx.x % CS;                          // K slice (= cluster rank)
+    const int js = blockIdx.x / CS;                          // unit group
     const int r0 = rs * KR;
     const unsigned ncta = gridDim.x;
     const int nks = KR / 16;
-    const int ksper = (nks + NW - 1) / NW;                   // <= 4
+    const int ksper = (nks + NW - 1) / NW;                   // <= KSMAX
     const int ks0 = w * ksper;
     const int myks = max(0, min(ksper, nks - ks0));
+    const size_t xstride = (size_t)NB * H4;
 
-    // A(m = unit, k = gate row) = W_hh[r, j] = whhT[j][r]; afr[mt][ks][4], 4 m-tiles of 16 units
-    uint32_t afr[4][4][4];
+    // The contraction index is ordered unit-major, r' = 4*j + g, so that a K-slice is produced by a
+    // contiguous range of CTAs (8 units x 4 gates each):  A(m = unit u, k = r') = W_hh[g*H + j, u]
+    // = whhT[u][g*H + j].  Consecutive k of a fragment register are gates (g, g+1) of the same j.
+    uint32_t afr[MT][KSMAX][4];
+    auto wpair = [&](int u, int rp) -> uint32_t {            // (r', r'+1), r' even
+        const int jj = rp >> 2, g = rp & 3;
+        const unsigned short lo = *reinterpret_cast<const unsigned short*>(p.whhT + (long)u * H4 + (long)g * H + jj);
+        const unsigned short hi = *reinterpret_cast<const unsigned short*>(p.whhT + (long)u * H4 + (long)(g + 1) * H + jj);
+        return (uint32_t)lo | ((uint32_t)hi << 16);
+    };
 #pragma unroll
-    for (int mt = 0; mt < 4; ++mt)
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
+        for (int ks = 0; ks < KSMAX; ++ks) {
             const int k = r0 + (ks0 + ks) * 16 + (l & 3) * 2;
             const int u = js * JS + mt * 16 + (l >> 2);
-            const __nv_bfloat16* rlo = p.whhT + (long)u * H4 + k;
-            const __nv_bfloat16* rhi = p.whhT + (long)(u + 8) * H4 + k;
             const bool ok = ks < myks;
-            afr[mt][ks][0] = ok ? ldg_u32(rlo) : 0u;
-            afr[mt][ks][1] = ok ? ldg_u32(rhi) : 0u;
-            afr[mt][ks][2] = ok ? ldg_u32(rlo + 8) : 0u;
-            afr[mt][ks][3] = ok ? ldg_u32(rhi + 8) : 0u;
+            afr[mt][ks][0] = ok ? wpair(u, k) : 0u;
+            afr[mt][ks][1] = ok ? wpair(u + 8, k) : 0u;
+            afr[mt][ks][2] = ok ? wpair(u, k + 8) : 0u;
+            afr[mt][ks][3] = ok ? wpair(u + 8, k + 8) : 0u;
         }
 
-    // phase-A ownership: unit = js*64 + rs*8 + w, batch = lane
-    const int j = js * JS + rs * 8 + w;
+    // phase-A ownership: unit = js*JS + rs*8 + w, batch = lane
+    const int j = js * JS + rs * UPC + w;
     const int bb = l;
     const bool own = bb < B;
     float dh = (own && p.dhT) ? p.dhT[(long)bb * H + j] : 0.f;
     float dc = (own && p.dcT) ? p.dcT[(long)bb * H + j] : 0.f;
-    __nv_bfloat16* gx[2] = {p.gx, p.gx + (size_t)NB * H4};
     unsigned epoch = 0;
 
+    // prefetched inputs of the gate-gradient math: gates i,f,g,o, c_t, c_{t-1}, dy_t
+    float in0 = 0.f, in1 = 0.f, in2 = 0.f, in3 = 0.f, in4 = 0.f, in5 = 0.f, in6 = 0.f;
+#define EB_PREFETCH(tt)                                                                                   \
+    if (own && (tt) >= 0) {                                                                               \
+        const long bt_ = (long)bb * T + (tt);                                                             \
+        const float* gp_ = p.gates + bt_ * H4 + j;                                                        \
+        in0 = __ldg(gp_); in1 = __ldg(gp_ + H); in2 = __ldg(gp_ + 2 * (long)H); in3 = __ldg(gp_ + 3 * (long)H); \
+        in4 = __ldg(p.cseq + bt_ * H + j);                                                                \
+        in5 = ((tt) > 0) ? __ldg(p.cseq + (bt_ - 1) * H + j) : (p.c0 ? p.c0[(long)bb * H + j] : 0.f);     \
+        in6 = __ldg(p.dy + bt_ * H + j);                                                                  \
+    }
+    EB_PREFETCH(T - 1)
+
     for (int t = T - 1; t >= 0; --t) {
-        __nv_bfloat16* gcur = gx[t & 1];
+        __nv_bfloat16* gcur = p.gx + (t & 1) * xstride;
         // ---- phase A: gate gradients of step t for the owned (unit, batch)
-        if (own) {
-            const long bt = (long)bb * T + t;
-            const float* gp = p.gates + bt * H4 + j;
-            const float ig = gp[0], fg = gp[H], gg = gp[2 * (long)H], og = gp[3 * (long)H];
-            const float ct = p.cseq[bt * H + j];
-            const float cprev = (t > 0) ? p.cseq[(bt - 1) * H + j] : (p.c0 ? p.c0[(long)bb * H + j] : 0.f);
-            const float tc = tanhf(ct);
-            const float dht = p.dy[bt * H + j] + dh;
-            const float dct = dc + dht * og * (1.f - tc * tc);
-            const float da[4] = {dct * gg * ig * (1.f - ig), dct * cprev * fg * (1.f - fg),
-                                 dct * ig * (1.f - gg * gg), dht * tc * og * (1.f - og)};
-            dc = dct * fg;
+        {
+            float da[4] = {0.f, 0.f, 0.f, 0.f};
+            if (own) {
+                const float ig = in0, fg = in1, gg = in2, og = in3;
+                const float tc = fast_tanh(in4);
+                const float dht = in6 + dh;
+                const float dct = dc + dht * og * (1.f - tc * tc);
+                da[0] = dct * gg * ig * (1.f - ig);
+                da[1] = dct * in5 * fg * (1.f - fg);
+                da[2] = dct * ig * (1.f - gg * gg);
+                da[3] = dht * tc * og * (1.f - og);
+                dc = dct * fg;
+            }
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
                 const __nv_bfloat16 v = __float2bfloat16(da[g]);
-                p.dg16[bt * H4 + (long)g * H + j] = v;
-                gcur[(long)bb * H4 + (long)g * H + j] = v;
+                sg[(bb * 4 + g) * UPC + w] = v;
+                sx[(bb * UPC + w) * 4 + g] = v;
             }
         }
-        __threadfence();
         __syncthreads();
-        if (tid == 0) atomicAdd(p.bar, 1u);
-        ++epoch;
-        warp_wait(p.bar, epoch * ncta);
-        // ---- phase B: partial dh_rec[unit (64), batch] over this CTA's K-slice of dG_t
-        {
-            const int chunks_per_row = myks * 2;
-            const int kbase = ks0 * 16;
-            for (int i = l; i < NB * chunks_per_row; i += 32) {
-                const int r = i / chunks_per_row, q = i % chunks_per_row;
-                cp_async16(gs + (size_t)r * KP + kbase + q * 8, gcur + (size_t)r * H4 + r0 + kbase + q * 8);
-            }
-            cp_async_wait_all();
-            __syncwarp();
+        if (tid < NB * 4) {   // 16-byte stores
+            const int b = tid >> 2, c = tid & 3;
+            const int jb = js * JS + rs * UPC;
+            // exchange buffer (unit-major): this CTA's 32 consecutive r' of batch row b, chunk c
+            *reinterpret_cast<uint4*>(gcur + (size_t)b * H4 + (size_t)jb * 4 + c * 8) =
+                *reinterpret_cast<const uint4*>(sx + (b * UPC) * 4 + c * 8);
+            // dG_t for the weight-gradient GEMMs (standard gate-major layout): gate c, 8 consecutive units
+            if (b < B) *reinterpret_cast<uint4*>(p.dg16 + ((size_t)b * T + t) * H4 + (size_t)c * H + jb) =
+                *reinterpret_cast<const uint4*>(sg + (b * 4 + c) * UPC);
         }
-        float acc[4][4][4];
+        __syncthreads();
+        ++epoch;
+        if (tid == 0) { __threadfence(); atomicAdd(p.bar, 1u); }
+        EB_PREFETCH(t - 1)                                   // overlaps the wait
+        if (tid == 0) spin_wait_ge(p.bar, epoch * ncta);     // one poller per CTA (see forward kernel)
+        __syncthreads();
+        // ---- phase B: partial dh_rec[unit (JS), batch] over this CTA's K-slice of dG_t
+        warp_pull(gs + ks0 * 16, KP, gcur + r0 + ks0 * 16, H4, myks * 2);
+        float acc[MT][4][4];
 #pragma unroll
-        for (int mt = 0; mt < 4; ++mt)
+        for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
                 for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
+        for (int ks = 0; ks < KSMAX; ++ks) {
             if (ks < myks) {
                 uint32_t b01[4], b23[4];
-                const int mrow = (l & 7) + ((l >> 4) & 1) * 8;
-                const int mk = (ks0 + ks) * 16 + ((l >> 3) & 1) * 8;
-                ldmatrix_x4(b01, gs + (size_t)mrow * KP + mk);
-                ldmatrix_x4(b23, gs + (size_t)(16 + mrow) * KP + mk);
+                load_b(b01, b23, gs, KP, ks0 + ks);
 #pragma unroll
-                for (int mt = 0; mt < 4; ++mt) {
+                for (int mt = 0; mt < MT; ++mt) {
                     mma_bf16(acc[mt][0], afr[mt][ks], b01[0], b01[1]);
                     mma_bf16(acc[mt][1], afr[mt][ks], b01[2], b01[3]);
                     mma_bf16(acc[mt][2], afr[mt][ks], b23[0], b23[1]);
@@ -341,51 +432,53 @@ __global__ void __launch_bounds__(NW * 32, 1) lstm_tc_bwd_kernel(BwdP p) {
         }
         // cross-warp reduction: red[w][slot][lane], slot = mt*16 + nt*4 + i
 #pragma unroll
-        for (int mt = 0; mt < 4; ++mt)
+        for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-                for (int i = 0; i < 4; ++i) red[(w * 64 + mt * 16 + nt * 4 + i) * 32 + l] = acc[mt][nt][i];
+                for (int i = 0; i < 4; ++i) red[(w * SLOTS + mt * 16 + nt * 4 + i) * 32 + l] = acc[mt][nt][i];
         __syncthreads();
-        // thread (w,l) sums slots [8w, 8w+8): slot -> (mt = slot/16, nt = (slot/4)%4, i = slot%4)
+        // SLOTS/NW slots per thread: slot -> (mt = slot/16, nt = (slot/4)%4, i = slot%4)
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const int slot = w * 8 + q;
+        for (int q = 0; q < SLOTS / NW; ++q) {
+            const int slot = w * (SLOTS / NW) + q;
             float s = 0.f;
 #pragma unroll
-            for (int sw = 0; sw < NW; ++sw) s += red[(sw * 64 + slot) * 32 + l];
+            for (int sw = 0; sw < NW; ++sw) s += red[(sw * SLOTS + slot) * 32 + l];
             const int mt = slot >> 4, nt = (slot >> 2) & 3, i = slot & 3;
             const int unit = mt * 16 + (l >> 2) + (i >> 1) * 8;
             const int bcol = nt * 8 + (l & 3) * 2 + (i & 1);
-            if (CLUSTER) part[unit * NB + bcol] = s;
-            else p.pglob[(((size_t)js * 8 + rs) * JS + unit) * NB + bcol] = s;
+            if (CLUSTER) part[((t & 1) * JS + unit) * NB + bcol] = s;
+            else p.pglob[((((size_t)(t & 1) * gridDim.x / CS + js) * CS + rs) * JS + unit) * NB + bcol] = s;
         }
         if (CLUSTER) {
             cg::cluster_group cluster = cg::this_cluster();
-            cluster.sync();                                 // all 8 partial tiles of the slice are visible
-            // reduce-scatter through distributed shared memory: this CTA finalises units [8*rs, 8*rs+8)
+            cluster.sync();                                 // all CS partial tiles of the group are visible
             float s = 0.f;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
+            for (int c = 0; c < CS; ++c) {
                 const float* rp = cluster.map_shared_rank(part, c);
-                s += rp[(rs * 8 + w) * NB + l];
+                s += rp[((t & 1) * JS + rs * UPC + w) * NB + l];
             }
             dh = s;                                          // dh_rec for (unit j, batch l) at step t-1
-            // `part` / `red` are rewritten only after the next grid barrier, which every CTA of the
-            // cluster reaches after finishing the remote reads above.
+            // `part` is double buffered by step parity: a buffer is rewritten two steps later, i.e.
+            // after another cluster.sync() that every reader passes only when done reading.
         } else {
-            __threadfence();
             __syncthreads();
-            if (tid == 0) atomicAdd(p.gbar + js, 1u);
-            warp_wait(p.gbar + js, 8u * (unsigned)(T - t));
+            if (tid == 0) {
+                __threadfence();
+                atomicAdd(p.gbar + js, 1u);
+                spin_wait_ge(p.gbar + js, (unsigned)CS * (unsigned)(T - t));
+            }
+            __syncthreads();
             float s = 0.f;
 #pragma unroll
-            for (int c = 0; c < 8; ++c)
-                s += __ldcg(p.pglob + (((size_t)js * 8 + c) * JS + rs * 8 + w) * NB + l);
+            for (int c = 0; c < CS; ++c)
+                s += __ldcg(p.pglob + ((((size_t)(t & 1) * gridDim.x / CS + js) * CS + c) * JS + rs * UPC + w) * NB + l);
             dh = s;
-            // pglob is rewritten one full grid barrier later (same argument as above)
         }
     }
+#undef EB_PREFETCH
     if (own) {
         p.dh0[(long)bb * H + j] = dh;
         p.dc0[(long)bb * H + j] = dc;
@@ -393,38 +486,96 @@ __global__ void __launch_bounds__(NW * 32, 1) lstm_tc_bwd_kernel(BwdP p) {
     if (CLUSTER) cg::this_cluster().sync();                  // no CTA exits while its smem may be read
 }
 
-inline bool tc_ok(int B, int H) { return H % JS == 0 && H <= 1024 && B >= 1; }
+inline bool tc_ok(int B, int H) { return H % 64 == 0 && H <= 1024 && B >= 1; }
+
+template <int CS>
+size_t bwd_smem(int H) {
+    return (size_t)NB * (4 * H / CS + PAD) * 2 + sizeof(float) * (NW * (CS / 2) * 16 * 32 + 2 * 8 * CS * NB) + 2 * NB * 4 * UPC * 2;
+}
+
+template <int CS>
+int max_clusters(int H) {
+    auto kern = lstm_tc_bwd_kernel<CS, true>;
+    const size_t smem = bwd_smem<CS>(H);
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return -2;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(H / 8);
+    cfg.blockDim = dim3(NW * 32);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = CS; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { (void)cudaGetLastError(); return -3; }
+    return n;
+}
+
+template <int CS>
+bool launch_cluster(const BwdP& p, int H, cudaStream_t st) {
+    auto kern = lstm_tc_bwd_kernel<CS, true>;
+    const size_t smem = bwd_smem<CS>(H);
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return false;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(H / 8);
+    cfg.blockDim = dim3(NW * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attrs[2];
+    attrs[0].id = cudaLaunchAttributeClusterDimension;
+    attrs[0].val.clusterDim.x = CS; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
+    attrs[1].id = cudaLaunchAttributeCooperative;
+    attrs[1].val.cooperative = 1;
+    cfg.attrs = attrs;
+    cfg.numAttrs = 2;
+    if (cudaLaunchKernelEx(&cfg, kern, p) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+    return true;
+}
+
+// cluster size to use for hidden size H: largest of 8/4/2 whose H/(8*CS) clusters are co-resident;
+// 0 = software (L2) reduction.  EDGEDICT_LSTM_CLUSTER=<0|2|4|8> overrides.
+int pick_cs(int H) {
+    static int cache[17];          // index H/64
+    static bool init = false;
+    if (!init) { for (int& c : cache) c = -1; init = true; }
+    int& c = cache[H / 64];
+    if (c >= 0) return c;
+    const char* e = getenv("EDGEDICT_LSTM_CLUSTER");
+    if (e) {
+        const int v = atoi(e);
+        c = (v == 8 || v == 4 || v == 2) ? v : 0;
+        return c;
+    }
+    if (max_clusters<8>(H) >= H / 64) c = 8;
+    else if (max_clusters<4>(H) >= H / 32) c = 4;
+    else if (max_clusters<2>(H) >= H / 16) c = 2;
+    else c = 0;
+    return c;
+}
 
 }  // namespace
 
 EB_API int eb_lstm_tc_supported(int B, int H) { return tc_ok(B, H) ? 1 : 0; }
 
-constexpr size_t TC_HDR = 1024;   // [0,256) grid barrier, [256,1024) per-slice barriers
-
 EB_API size_t eb_lstm_tc_scratch_bytes(int B, int H) {
     if (!tc_ok(B, H)) return 0;
-    return TC_HDR + sizeof(__nv_bfloat16) * (size_t)2 * NB * 4 * H + sizeof(float) * (size_t)(H / JS) * 8 * JS * NB;
+    return TC_HDR + sizeof(__nv_bfloat16) * (size_t)2 * NB * 4 * H + sizeof(float) * (size_t)2 * (H / 8) * 64 * NB;
 }
 
-// how many 8-CTA clusters of the BPTT kernel can be co-resident (diagnostic + path selection)
-EB_API int eb_lstm_tc_max_clusters(int H) {
-    if (H % JS || H > 1024) return -1;
-    const int KR = 4 * H / 8;
-    const size_t smem = (size_t)NB * (KR + PAD) * 2 + sizeof(float) * (NW * 64 * 32 + JS * NB);
-    if (cudaFuncSetAttribute(lstm_tc_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-        return -2;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((H / JS) * 8);
-    cfg.blockDim = dim3(NW * 32);
-    cfg.dynamicSmemBytes = smem;
-    cudaLaunchAttribute attr;
-    attr.id = cudaLaunchAttributeClusterDimension;
-    attr.val.clusterDim.x = 8; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
-    cfg.attrs = &attr;
-    cfg.numAttrs = 1;
-    int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, lstm_tc_bwd_kernel<true>, &cfg) != cudaSuccess) { (void)cudaGetLastError(); return -3; }
-    return n;
+// co-resident clusters of `cs` CTAs of the BPTT kernel (diagnostic + path selection)
+EB_API int eb_lstm_tc_max_clusters(int H, int cs) {
+    if (H % 64 || H > 1024) return -1;
+    if (cs == 8) return max_clusters<8>(H);
+    if (cs == 4) return max_clusters<4>(H);
+    if (cs == 2) return max_clusters<2>(H);
+    return -1;
 }
 
 // xg [B,T,4H] fp32; whh16 [4H,H] bf16.  B > 32 is processed in batch tiles of 32 (independent
@@ -434,7 +585,7 @@ EB_API int eb_lstm_tc_fwd(const float* xg, const void* whh16, const float* h0, c
                           void* scratch, int B, int T, int H, void* stream) {
     if (!xg || !whh16 || !y || !hT || !cT || !scratch || T <= 0 || !tc_ok(B, H)) return EB_ERR_INVALID;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const size_t smem = (size_t)NB * (H + PAD) * 2 + sizeof(float) * NW * 32 * 32;
+    const size_t smem = (size_t)NB * (H + PAD) * 2 + sizeof(float) * NW * 32 * 32 + NB * UPC * 2;
     EB_CUDA(cudaFuncSetAttribute(lstm_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int b0 = 0; b0 < B; b0 += NB) {
         const int nb = (B - b0 < NB) ? (B - b0) : NB;
@@ -452,6 +603,7 @@ EB_API int eb_lstm_tc_fwd(const float* xg, const void* whh16, const float* h0, c
         p.bar = reinterpret_cast<unsigned*>(scratch);
         p.hx = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(scratch) + TC_HDR);
         p.B = nb; p.T = T; p.H = H;
+        { const char* e = getenv("EDGEDICT_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
         EB_CUDA(cudaMemsetAsync(scratch, 0, TC_HDR + sizeof(__nv_bfloat16) * (size_t)2 * NB * H, st));
         void* args[] = {&p};
         EB_CUDA(cudaLaunchCooperativeKernel((void*)lstm_tc_fwd_kernel, dim3(H / UPC), dim3(NW * 32), args, smem, st));
@@ -466,18 +618,7 @@ EB_API int eb_lstm_tc_bwd(const float* dy, const float* gates, const float* cseq
     if (!dy || !gates || !cseq || !whhT16 || !dg16 || !dh0 || !dc0 || !scratch || T <= 0 || !tc_ok(B, H))
         return EB_ERR_INVALID;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const int KR = 4 * H / 8;
-    const size_t smem = (size_t)NB * (KR + PAD) * 2 + sizeof(float) * (NW * 64 * 32 + JS * NB);
-    const int nclusters = H / JS;
-    static int use_cluster = -1;            // decided once: env override, else occupancy query
-    if (use_cluster < 0) {
-        const char* e = getenv("EDGEDICT_LSTM_CLUSTER");
-        if (e) use_cluster = atoi(e) ? 1 : 0;
-        else use_cluster = (eb_lstm_tc_max_clusters(1024) >= 16) ? 1 : 0;
-    }
-    bool cluster = use_cluster == 1 && eb_lstm_tc_max_clusters(H) >= nclusters;
-    EB_CUDA(cudaFuncSetAttribute(lstm_tc_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    EB_CUDA(cudaFuncSetAttribute(lstm_tc_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int cs = pick_cs(H);
     char* base = reinterpret_cast<char*>(scratch);
     for (int b0 = 0; b0 < B; b0 += NB) {
         const int nb = (B - b0 < NB) ? (B - b0) : NB;
@@ -493,33 +634,22 @@ EB_API int eb_lstm_tc_bwd(const float* dy, const float* gates, const float* cseq
         p.dh0 = dh0 + (size_t)b0 * H;
         p.dc0 = dc0 + (size_t)b0 * H;
         p.bar = reinterpret_cast<unsigned*>(base);
-        p.gbar = reinterpret_cast<unsigned*>(base + 256);
+        p.gbar = reinterpret_cast<unsigned*>(base + 1024);
         p.gx = reinterpret_cast<__nv_bfloat16*>(base + TC_HDR);
         p.pglob = reinterpret_cast<float*>(base + TC_HDR + sizeof(__nv_bfloat16) * (size_t)2 * NB * 4 * H);
         p.B = nb; p.T = T; p.H = H;
         EB_CUDA(cudaMemsetAsync(scratch, 0, TC_HDR + sizeof(__nv_bfloat16) * (size_t)2 * NB * 4 * H, st));
         bool launched = false;
-        if (cluster) {
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(nclusters * 8);
-            cfg.blockDim = dim3(NW * 32);
-            cfg.dynamicSmemBytes = smem;
-            cfg.stream = st;
-            cudaLaunchAttribute attrs[2];
-            attrs[0].id = cudaLaunchAttributeClusterDimension;
-            attrs[0].val.clusterDim.x = 8; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
-            attrs[1].id = cudaLaunchAttributeCooperative;
-            attrs[1].val.cooperative = 1;
-            cfg.attrs = attrs;
-            cfg.numAttrs = 2;
-            cudaError_t e = cudaLaunchKernelEx(&cfg, lstm_tc_bwd_kernel<true>, p);
-            if (e == cudaSuccess) launched = true;
-            else { (void)cudaGetLastError(); cluster = false; use_cluster = 0; }   // never launch un-guaranteed
-        }
+        if (cs == 8) launched = launch_cluster<8>(p, H, st);
+        else if (cs == 4) launched = launch_cluster<4>(p, H, st);
+        else if (cs == 2) launched = launch_cluster<2>(p, H, st);
         if (!launched) {
+            // software reduce-scatter through L2: plain cooperative grid, always co-resident
+            auto kern = lstm_tc_bwd_kernel<4, false>;
+            const size_t smem = bwd_smem<4>(H);
+            EB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             void* args[] = {&p};
-            EB_CUDA(cudaLaunchCooperativeKernel((void*)lstm_tc_bwd_kernel<false>, dim3(nclusters * 8), dim3(NW * 32),
-                                                args, smem, st));
+            EB_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(H / 8), dim3(NW * 32), args, smem, st));
         }
     }
     return EB_OK;

@@ -69,7 +69,7 @@ int eb_lstm_seq_bwd(const float* dy, const float* gates, const float* cseq, cons
  * [B,T,4H] bf16 gate-preactivation gradients. */
 int eb_lstm_tc_supported(int B, int H);
 size_t eb_lstm_tc_scratch_bytes(int B, int H);
-int eb_lstm_tc_max_clusters(int H);   /* co-resident 8-CTA clusters of the BPTT kernel (diagnostic) */
+int eb_lstm_tc_max_clusters(int H, int cluster_size);   /* co-resident clusters of the BPTT kernel (diagnostic) */
 int eb_lstm_tc_fwd(const float* xg, const void* whh16, const float* h0, const float* c0, float* y, void* y16,
                    float* hT, float* cT, float* gates_save, float* cseq_save, void* scratch, int B, int T,
                    int H, void* stream);

@@ -5,11 +5,11 @@ python - > gpurun_out/tc_probe.log 2>&1 <<'PY'
 from edgedict_b200._lib import lib
 L = lib()
 for H in (64, 256, 320, 512, 1024):
-    print("H", H, "max co-resident clusters of 8:", L.eb_lstm_tc_max_clusters(H), "needed", H // 64)
+    print("H", H, "co-resident clusters (size: max/needed):", {cs: (L.eb_lstm_tc_max_clusters(H, cs), H // (8 * cs)) for cs in (8, 4, 2)})
 PY
 cat gpurun_out/tc_probe.log
-for mode in 0 1; do
-  for case in "4 6 32 64" "32 9 64 256" "32 4 64 1024" "32 50 64 1024"; do
+for mode in ${TC_MODES:-0 2 4 8}; do
+  for case in "4 6 32 64" "32 9 64 256" "32 4 64 1024" "32 500 64 1024"; do
     set -- $case
     EDGEDICT_LSTM_CLUSTER=$mode timeout 90 python - $1 $2 $3 $4 >> gpurun_out/tc_debug.log 2>&1 <<'PY'
 import sys, os, time, numpy as np, torch
@@ -32,6 +32,18 @@ print("mode", os.environ["EDGEDICT_LSTM_CLUSTER"], (B, T, I, H), "fwd ok %.3fs" 
 (y * dy.cuda()).sum().backward()
 torch.cuda.synchronize()
 print("   bwd ok %.3fs" % (time.time()-t0), flush=True)
+if T >= 100:
+    for name, fn in (("fwd", lambda: Fn.LSTMLayer.apply(ins[0], None, None, ins[1], ins[2], ins[3], ins[4], "bf16")),):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ops.PROF.reset(); ops.PROF.enabled = True
+        for _ in range(3):
+            yy, _, _ = fn()
+            (yy * dy.cuda()).sum().backward()
+        torch.cuda.synchronize()
+        for k, v in ops.PROF.summary().items():
+            if k.startswith("lstm"):
+                print("   %s: %.3f ms/call -> %.2f us/step" % (k, v["ms"] / v["calls"], v["ms"] / v["calls"] / T * 1e3), flush=True)
+        ops.PROF.enabled = False
 if T <= 10:
     ref = [t.double().requires_grad_(True) for t in (x, w_ih, w_hh, b_ih, b_hh)]
     yr, _, _ = mt.lstm_layer(ref[0], torch.zeros(B, H).double(), torch.zeros(B, H).double(), *ref[1:])
