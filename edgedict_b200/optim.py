@@ -20,20 +20,22 @@ class FlatAdam:
         dev = params[0].device
         if dev.type != "cuda":
             raise RuntimeError("FlatAdam needs the module on a CUDA device")
-        n = sum(p.numel() for p in params)
+        # every parameter starts on a 16-byte boundary of the bucket (vector loads, TMA-friendly)
+        offs, n = [], 0
+        for p in params:
+            offs.append(n)
+            n += (p.numel() + 3) // 4 * 4
         self.n = n
-        self.flat_params = torch.empty(n, dtype=torch.float32, device=dev)
+        self.flat_params = torch.zeros(n, dtype=torch.float32, device=dev)
         self.flat_grads = torch.zeros(n, dtype=torch.float32, device=dev)
         self.m = torch.zeros(n, dtype=torch.float32, device=dev)
         self.v = torch.zeros(n, dtype=torch.float32, device=dev)
-        off = 0
         with torch.no_grad():
-            for p in params:
+            for p, off in zip(params, offs):
                 k = p.numel()
                 self.flat_params[off:off + k].copy_(p.reshape(-1))
                 p.data = self.flat_params[off:off + k].view(p.shape)
                 p.grad = self.flat_grads[off:off + k].view(p.shape)
-                off += k
         self.params = params
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.step_count = 0
