@@ -271,6 +271,10 @@ def main():
                                        d2h_bytes_per_step=0))))
         return
     out = run_ours(args)
+    import torch.distributed as dist
+    if dist.is_initialized():
+        dist.barrier()
+        dist.destroy_process_group()
     if out is None:
         return
     if args.gpus == 1 and not args.no_cpu_baseline:
