@@ -16,17 +16,27 @@
 //   TMEM: 2 accumulator buffers x 128 fp32 columns, so the epilogue of tile i overlaps the
 //   mainloop of tile i+1.
 #include <cuda.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "../../include/edgedict_b200.h"
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 64, STAGES = 5, UMMA_K = 16;
-constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int BM = 128, BK = 64, UMMA_K = 16;
+constexpr int A_BYTES = BM * BK * 2;
 constexpr int EPI_BYTES = 4 * 32 * 36 * 4;
-constexpr int TMEM_COLS = 256;
-constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + EPI_BYTES + 256;
 constexpr int NTHREADS = 192;
+// Tile width BN_ = 128 (5 stages, 2 x 128 TMEM columns) or 256 (4 stages, 2 x 256 = all 512 TMEM
+// columns).  A 128 x 128 x 16 MMA reads 8 KB of shared memory in 64 cycles = the 128 B/clk limit of
+// the SM; the 128 x 256 tile reads 12 KB in 128 cycles, which leaves headroom for the TMA writes.
+template <int BN_> struct Cfg {
+    static constexpr int BN = BN_;
+    static constexpr int STAGES = BN_ == 256 ? 4 : 5;
+    static constexpr int B_BYTES = BN_ * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int TMEM_COLS = 2 * BN_;
+    static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + EPI_BYTES + 256;
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -122,11 +132,13 @@ struct Sched {
 // A_MN / B_MN: operand stored with its M (resp. N) index contiguous ("MN-major"), else K contiguous.
 //   K-major tile in smem : [128 rows][64 k] bf16, 128 B per row, 128B swizzle; SBO = 1024 (8 rows)
 //   MN-major tile in smem: 2 x [64 k][64 mn] bf16, 128 B per k-row; SBO = 1024 (8 k-rows), LBO = 8192
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, int BN_>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                void* __restrict__ Cout, int c_bf16, const float* __restrict__ bias, int accumulate,
                long M, int N, long K, int ksplit) {
+    constexpr int BN = BN_, STAGES = Cfg<BN_>::STAGES, STAGE_BYTES = Cfg<BN_>::STAGE_BYTES;
+    constexpr int TMEM_COLS = Cfg<BN_>::TMEM_COLS;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* tiles = smem;
@@ -178,7 +190,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     if (!A_MN) tma_load_2d(sa, &tma_a, kb * BK, m0, fb);
                     else { tma_load_2d(sa, &tma_a, m0, kb * BK, fb); tma_load_2d(sa + 8192, &tma_a, m0 + 64, kb * BK, fb); }
                     if (!B_MN) tma_load_2d(sb, &tma_b, kb * BK, n0, fb);
-                    else { tma_load_2d(sb, &tma_b, n0, kb * BK, fb); tma_load_2d(sb + 8192, &tma_b, n0 + 64, kb * BK, fb); }
+                    else {
+#pragma unroll
+                        for (int bx = 0; bx < BN / 64; ++bx) tma_load_2d(sb + bx * 8192, &tma_b, n0 + bx * 64, kb * BK, fb);
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -354,9 +369,10 @@ bool make_map(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer,
     return r == CUDA_SUCCESS;
 }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, int BN_>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, void* C, int c_bf16, const float* bias, int accumulate,
            long M, int N, long K, cudaStream_t st) {
+    constexpr int BN = BN_;
     const long out_tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     const long nkb = (K + BK - 1) / BK;
     // split-K (weight gradients: few output tiles, contraction over millions of rows): fill the
@@ -369,15 +385,15 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, void* C, int c_bf16, co
         if (ksplit < 1) ksplit = 1;
     }
     if (ksplit > 1 && !accumulate) EB_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, st));
-    auto kern = gemm_tc_kernel<A_MN, B_MN>;
+    auto kern = gemm_tc_kernel<A_MN, B_MN, BN_>;
     static bool attr_done = false;
     if (!attr_done) {
-        EB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        EB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN_>::SMEM_BYTES));
         attr_done = true;
     }
     const long tiles = out_tiles * ksplit;
     const int grid = (int)(tiles < eb_num_sms() ? tiles : eb_num_sms());
-    kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(ta, tb, C, c_bf16, bias, accumulate, M, N, K, ksplit);
+    kern<<<grid, NTHREADS, Cfg<BN_>::SMEM_BYTES, st>>>(ta, tb, C, c_bf16, bias, accumulate, M, N, K, ksplit);
     EB_CHECK_LAUNCH();
     return EB_OK;
 }
@@ -390,18 +406,30 @@ EB_API int eb_gemm_bf16(const void* A, int a_mn_major, const void* B, int b_mn_m
     if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return EB_ERR_INVALID;
     // contiguous dimension must keep row pitches 16-byte aligned
     if ((a_mn_major ? M : K) % 8 || (b_mn_major ? (long)N : K) % 8) return EB_ERR_INVALID;
+    // 256-wide tiles when they tile N exactly and there is enough work to fill the machine with them
+    static int force_bn = -1;
+    if (force_bn < 0) { const char* e = getenv("EDGEDICT_GEMM_BN"); force_bn = e ? atoi(e) : 0; }
+    const long wide_tiles = ((M + BM - 1) / BM) * (N / 256);
+    bool wide = (N % 256 == 0) && (wide_tiles >= eb_num_sms() || (!c_bf16 && (K + BK - 1) / BK >= 64 && wide_tiles * 4 >= eb_num_sms()));
+    if (force_bn == 128) wide = false;
+    if (force_bn == 256 && N % 256 == 0) wide = true;
     CUtensorMap ta, tb;
     bool ok = a_mn_major ? make_map(&ta, A, (uint64_t)M, (uint64_t)K, 64) : make_map(&ta, A, (uint64_t)K, (uint64_t)M, 128);
-    ok = ok && (b_mn_major ? make_map(&tb, B, (uint64_t)N, (uint64_t)K, 64) : make_map(&tb, B, (uint64_t)K, (uint64_t)N, 128));
+    ok = ok && (b_mn_major ? make_map(&tb, B, (uint64_t)N, (uint64_t)K, 64)
+                           : make_map(&tb, B, (uint64_t)K, (uint64_t)N, wide ? 256 : 128));
     if (!ok) {
         fprintf(stderr, "[edgedict_b200] cuTensorMapEncodeTiled failed\n");
         return EB_ERR_CUDA;
     }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+#define EB_GO(AM, BMN)                                                                              \
+    return wide ? launch<AM, BMN, 256>(ta, tb, C, c_bf16, bias, accumulate, M, N, K, st)           \
+                : launch<AM, BMN, 128>(ta, tb, C, c_bf16, bias, accumulate, M, N, K, st)
     if (a_mn_major) {
-        if (b_mn_major) return launch<true, true>(ta, tb, C, c_bf16, bias, accumulate, M, N, K, st);
-        return launch<true, false>(ta, tb, C, c_bf16, bias, accumulate, M, N, K, st);
+        if (b_mn_major) { EB_GO(true, true); }
+        EB_GO(true, false);
     }
-    if (b_mn_major) return launch<false, true>(ta, tb, C, c_bf16, bias, accumulate, M, N, K, st);
-    return launch<false, false>(ta, tb, C, c_bf16, bias, accumulate, M, N, K, st);
+    if (b_mn_major) { EB_GO(false, true); }
+    EB_GO(false, false);
+#undef EB_GO
 }
