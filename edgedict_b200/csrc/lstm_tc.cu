@@ -34,7 +34,7 @@ namespace {
 constexpr int NW = 8;            // warps per CTA
 constexpr int UPC = 8;           // hidden units finalised per CTA
 constexpr int PAD = 8;           // bf16 elements of row padding (16 B) -> conflict-free ldmatrix
-constexpr int NB = 32;           // batch tile
+constexpr int NB = 32;           // widest batch tile (rows of the exchange buffers)
 constexpr size_t TC_HDR = 2048;  // scratch: [0,1024) grid barrier counter, [1024,2048) per-group barriers
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -65,7 +65,7 @@ __device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.
 // one warp copies its K-range (cpr 16-byte chunks per row, NB rows) of the exchange buffer into a
 // padded shared tile.  No integer division in the common case (cpr divides 32).
 __device__ __forceinline__ void warp_pull(__nv_bfloat16* dst, int dst_ld, const __nv_bfloat16* src, int src_ld,
-                                          int cpr) {
+                                          int cpr, int nrows) {
     const int l = threadIdx.x & 31;
     if (cpr > 0 && (32 % cpr) == 0) {
         const int rstep = 32 / cpr;
@@ -73,13 +73,13 @@ __device__ __forceinline__ void warp_pull(__nv_bfloat16* dst, int dst_ld, const 
         const int q = l % cpr;
         __nv_bfloat16* d = dst + (size_t)r * dst_ld + q * 8;
         const __nv_bfloat16* g = src + (size_t)r * src_ld + q * 8;
-        for (; r < NB; r += rstep) {
+        for (; r < nrows; r += rstep) {
             cp_async16(d, g);
             d += (size_t)rstep * dst_ld;
             g += (size_t)rstep * src_ld;
         }
     } else {
-        for (int i = l; i < NB * cpr; i += 32) {
+        for (int i = l; i < nrows * cpr; i += 32) {
             const int r = i / cpr, q = i % cpr;
             cp_async16(dst + (size_t)r * dst_ld + q * 8, src + (size_t)r * src_ld + q * 8);
         }
@@ -114,13 +114,14 @@ __device__ __forceinline__ void warp_release(unsigned* ctr) {
     }
 }
 // B fragments for one k-step and all four batch n-tiles out of a padded [NB][ld] bf16 tile
+template <int NT>
 __device__ __forceinline__ void load_b(uint32_t (&b01)[4], uint32_t (&b23)[4], const __nv_bfloat16* tile, int ld,
                                        int kstep) {
     const int l = threadIdx.x & 31;
     const int mrow = (l & 7) + ((l >> 4) & 1) * 8;
     const int mk = kstep * 16 + ((l >> 3) & 1) * 8;
     ldmatrix_x4(b01, tile + (size_t)mrow * ld + mk);
-    ldmatrix_x4(b23, tile + (size_t)(16 + mrow) * ld + mk);
+    if (NT > 2) ldmatrix_x4(b23, tile + (size_t)(16 + mrow) * ld + mk);
 }
 
 struct FwdP {
@@ -135,13 +136,33 @@ struct FwdP {
                                   // 4 skip non-critical stores, 8 single poller, 16 skip fence
 };
 
-__global__ void __launch_bounds__(NW * 32, 1) lstm_tc_fwd_kernel(FwdP p) {
+// NBT = batch rows per CTA.  NBT = 16: the batch tile of 32 is split into two independent halves
+// (blockIdx.y) whose CTAs are co-resident two per SM -- two independent recurrences interleave on
+// every SM and hide each other's barrier / exchange latency (the per-step critical path is latency,
+// not throughput: ~1 of 4 issue slots is used).
+template <int NBT>
+__global__ void __launch_bounds__(NW * 32, (NBT == 16) ? 2 : 1) lstm_tc_fwd_kernel(FwdP p) {
+    constexpr int NT = NBT / 8;                              // batch n-tiles
+    constexpr int SL = NT * 8;                               // accumulator slots per thread
+    const int hb = blockIdx.y;                               // which batch tile
+    p.xg += (size_t)hb * NBT * p.T * 4 * p.H;
+    p.y += (size_t)hb * NBT * p.T * p.H;
+    if (p.y16) p.y16 += (size_t)hb * NBT * p.T * p.H;
+    if (p.gates) p.gates += (size_t)hb * NBT * p.T * 4 * p.H;
+    if (p.cseq) p.cseq += (size_t)hb * NBT * p.T * p.H;
+    if (p.h0) p.h0 += (size_t)hb * NBT * p.H;
+    if (p.c0) p.c0 += (size_t)hb * NBT * p.H;
+    p.hT += (size_t)hb * NBT * p.H;
+    p.cT += (size_t)hb * NBT * p.H;
+    p.hx += (size_t)hb * 2 * NBT * p.H;
+    p.bar += hb * 64;
+    p.B = min(NBT, p.B - hb * NBT);
     extern __shared__ __align__(16) unsigned char smraw[];
     const int H = p.H, B = p.B, T = p.T;
     const int HP = H + PAD;
-    __nv_bfloat16* hs = reinterpret_cast<__nv_bfloat16*>(smraw);                 // [NB][HP]
-    float* red = reinterpret_cast<float*>(smraw + (size_t)NB * HP * 2);          // [NW][32][32]
-    __nv_bfloat16* sh_h = reinterpret_cast<__nv_bfloat16*>(red + NW * 32 * 32);  // [NB][UPC]
+    __nv_bfloat16* hs = reinterpret_cast<__nv_bfloat16*>(smraw);                 // [NBT][HP]
+    float* red = reinterpret_cast<float*>(smraw + (size_t)NBT * HP * 2);         // [NW][SL][32]
+    __nv_bfloat16* sh_h = reinterpret_cast<__nv_bfloat16*>(red + NW * SL * 32);   // [NBT][UPC]
     const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
     const int j0 = blockIdx.x * UPC;
     const unsigned ncta = gridDim.x;
@@ -149,7 +170,7 @@ __global__ void __launch_bounds__(NW * 32, 1) lstm_tc_fwd_kernel(FwdP p) {
     const int ksper = (nks + NW - 1) / NW;                   // <= 8
     const int ks0 = w * ksper;
     const int myks = max(0, min(ksper, nks - ks0));
-    const size_t xstride = (size_t)NB * H;
+    const size_t xstride = (size_t)NBT * H;
 
     // resident A fragments: afr[mt][ks][4]; mt 0 = rows (i: 0-7, f: 8-15), mt 1 = (g, o)
     uint32_t afr[2][8][4];
@@ -172,7 +193,7 @@ __global__ void __launch_bounds__(NW * 32, 1) lstm_tc_fwd_kernel(FwdP p) {
     const int ju = l >> 2;
     const int bb = (w >> 1) * 8 + (l & 3) * 2 + (w & 1);
     const int j = j0 + ju;
-    const bool own = bb < B;
+    const bool own = (w >> 1) < NT && bb < B;
     float c_state = (own && p.c0) ? p.c0[(long)bb * H + j] : 0.f;
     if (own) p.hx[xstride + (long)bb * H + j] = __float2bfloat16(p.h0 ? p.h0[(long)bb * H + j] : 0.f);
     __syncthreads();
@@ -202,25 +223,27 @@ __global__ void __launch_bounds__(NW * 32, 1) lstm_tc_fwd_kernel(FwdP p) {
             __syncthreads();
         }
         // pull this warp's K-range of h_{t-1}: NB rows x (myks*16) bf16
-        if (!(p.dbg & 2)) warp_pull(hs + ks0 * 16, HP, hprev + ks0 * 16, H, myks * 2);
-        float acc[2][4][4];
+        if (!(p.dbg & 2)) warp_pull(hs + ks0 * 16, HP, hprev + ks0 * 16, H, myks * 2, NBT);
+        float acc[2][NT][4];
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt)
+            for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
                 for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
             if (ks < myks && !(p.dbg & 2)) {
                 uint32_t b01[4], b23[4];
-                load_b(b01, b23, hs, HP, ks0 + ks);
+                load_b<NT>(b01, b23, hs, HP, ks0 + ks);
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt) {
                     mma_bf16(acc[mt][0], afr[mt][ks], b01[0], b01[1]);
                     mma_bf16(acc[mt][1], afr[mt][ks], b01[2], b01[3]);
-                    mma_bf16(acc[mt][2], afr[mt][ks], b23[0], b23[1]);
-                    mma_bf16(acc[mt][3], afr[mt][ks], b23[2], b23[3]);
+                    if (NT > 2) {
+                        mma_bf16(acc[mt][NT - 2], afr[mt][ks], b23[0], b23[1]);
+                        mma_bf16(acc[mt][NT - 1], afr[mt][ks], b23[2], b23[3]);
+                    }
                 }
             }
         }
@@ -228,17 +251,17 @@ __global__ void __launch_bounds__(NW * 32, 1) lstm_tc_fwd_kernel(FwdP p) {
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt)
+            for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-                for (int i = 0; i < 4; ++i) red[(w * 32 + nt * 8 + mt * 4 + i) * 32 + l] = acc[mt][nt][i];
+                for (int i = 0; i < 4; ++i) red[(w * SL + nt * 8 + mt * 4 + i) * 32 + l] = acc[mt][nt][i];
         __syncthreads();
         float ig = 0.f, fg = 0.f, gg = 0.f, og = 0.f, hn = 0.f;
-        {   // nt = w>>1, batch offset = w&1 -> slots (i: mt0,c=off) (f: mt0,c=2+off) (g: mt1,off) (o: mt1,2+off)
+        if ((w >> 1) < NT) {   // nt = w>>1, batch offset = w&1 -> slots (i: mt0,off) (f: mt0,2+off) (g: mt1,off) (o: mt1,2+off)
             const int nt = w >> 1, off = w & 1;
             float s[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int sw = 0; sw < NW; ++sw) {
-                const float* r = red + (size_t)(sw * 32 + nt * 8) * 32 + l;
+                const float* r = red + (size_t)(sw * SL + nt * 8) * 32 + l;
                 s[0] += r[(0 + off) * 32];
                 s[1] += r[(2 + off) * 32];
                 s[2] += r[(4 + off) * 32];
@@ -254,7 +277,7 @@ __global__ void __launch_bounds__(NW * 32, 1) lstm_tc_fwd_kernel(FwdP p) {
         }
         __syncthreads();
         if (w == 0) {   // publish h_t: one 16-byte store per batch row, then a single fence + arrive
-            *reinterpret_cast<uint4*>(hnext + (size_t)l * H + j0) = *reinterpret_cast<const uint4*>(sh_h + l * UPC);
+            if (l < NBT) *reinterpret_cast<uint4*>(hnext + (size_t)l * H + j0) = *reinterpret_cast<const uint4*>(sh_h + l * UPC);
             __syncwarp();
             if (l == 0) {
                 if (p.dbg & 16) atomicAdd(p.bar, 1u);                                   // (unsafe reference point)
@@ -408,7 +431,7 @@ __global__ void __launch_bounds__(NW * 32, 1) lstm_tc_bwd_kernel(BwdP p) {
         if (tid == 0) spin_wait_ge(p.bar, epoch * ncta);     // one poller per CTA (see forward kernel)
         __syncthreads();
         // ---- phase B: partial dh_rec[unit (JS), batch] over this CTA's K-slice of dG_t
-        warp_pull(gs + ks0 * 16, KP, gcur + r0 + ks0 * 16, H4, myks * 2);
+        warp_pull(gs + ks0 * 16, KP, gcur + r0 + ks0 * 16, H4, myks * 2, NB);
         float acc[MT][4][4];
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt)
@@ -420,7 +443,7 @@ __global__ void __launch_bounds__(NW * 32, 1) lstm_tc_bwd_kernel(BwdP p) {
         for (int ks = 0; ks < KSMAX; ++ks) {
             if (ks < myks) {
                 uint32_t b01[4], b23[4];
-                load_b(b01, b23, gs, KP, ks0 + ks);
+                load_b<4>(b01, b23, gs, KP, ks0 + ks);
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt) {
                     mma_bf16(acc[mt][0], afr[mt][ks], b01[0], b01[1]);
@@ -585,8 +608,26 @@ EB_API int eb_lstm_tc_fwd(const float* xg, const void* whh16, const float* h0, c
                           void* scratch, int B, int T, int H, void* stream) {
     if (!xg || !whh16 || !y || !hT || !cT || !scratch || T <= 0 || !tc_ok(B, H)) return EB_ERR_INVALID;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const size_t smem = (size_t)NB * (H + PAD) * 2 + sizeof(float) * NW * 32 * 32 + NB * UPC * 2;
-    EB_CUDA(cudaFuncSetAttribute(lstm_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // batch tile of 16 rows, two tiles co-resident per SM (see kernel comment), unless disabled or
+    // the occupancy query says two CTAs do not fit
+    static int split = -1;
+    if (split < 0) {
+        const char* e = getenv("EDGEDICT_LSTM_SPLIT");
+        split = e ? (atoi(e) ? 1 : 0) : 0;     // measured: no gain (each half is as latency-bound as the whole), off by default
+        if (split) {
+            int nblk = 0;
+            const size_t sm16 = (size_t)16 * (1024 + PAD) * 2 + sizeof(float) * NW * 16 * 32 + 16 * UPC * 2;
+            cudaFuncSetAttribute(lstm_tc_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm16);
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, lstm_tc_fwd_kernel<16>, NW * 32, sm16) != cudaSuccess || nblk < 2) {
+                (void)cudaGetLastError();
+                split = 0;
+            }
+        }
+    }
+    const int nbt = split ? 16 : 32;
+    const size_t smem = (size_t)nbt * (H + PAD) * 2 + sizeof(float) * NW * (nbt / 8) * 8 * 32 + nbt * UPC * 2;
+    if (split) EB_CUDA(cudaFuncSetAttribute(lstm_tc_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else EB_CUDA(cudaFuncSetAttribute(lstm_tc_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int b0 = 0; b0 < B; b0 += NB) {
         const int nb = (B - b0 < NB) ? (B - b0) : NB;
         FwdP p;
@@ -606,7 +647,9 @@ EB_API int eb_lstm_tc_fwd(const float* xg, const void* whh16, const float* h0, c
         { const char* e = getenv("EDGEDICT_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
         EB_CUDA(cudaMemsetAsync(scratch, 0, TC_HDR + sizeof(__nv_bfloat16) * (size_t)2 * NB * H, st));
         void* args[] = {&p};
-        EB_CUDA(cudaLaunchCooperativeKernel((void*)lstm_tc_fwd_kernel, dim3(H / UPC), dim3(NW * 32), args, smem, st));
+        const int ntiles = (nb + nbt - 1) / nbt;
+        if (split) EB_CUDA(cudaLaunchCooperativeKernel((void*)lstm_tc_fwd_kernel<16>, dim3(H / UPC, ntiles), dim3(NW * 32), args, smem, st));
+        else EB_CUDA(cudaLaunchCooperativeKernel((void*)lstm_tc_fwd_kernel<32>, dim3(H / UPC, ntiles), dim3(NW * 32), args, smem, st));
     }
     return EB_OK;
 }
