@@ -166,14 +166,20 @@ def _joint_pre(h_enc, h_dec, w1, b1, precision):
     return he2, hd2, ep, dp
 
 
-def _joint_bwd(ctx_p, dlog2, hid, he2, hd2, w1, w2, dims, need_w=True):
-    """Shared backward of the joint given d logits [N_cells, V] (fp32 or bf16)."""
+def _joint_bwd(ctx_p, dlog2, hid, he2, hd2, w1, w2, dims, db2=None):
+    """Shared backward of the joint given d logits [N_cells, V] (fp32 or bf16); db2 may already have
+    been accumulated by the fused loss-gradient kernel."""
     B, T, U, E, Dd, J, V = dims
     p = ctx_p
     dl16 = dlog2 if dlog2.dtype == bf16 else (ops.cast_bf16(dlog2) if p == "bf16" else None)
-    db2 = ops.colsum(dlog2)
+    if db2 is None:
+        db2 = ops.colsum(dlog2)
     hid2 = hid.view(B * T * U, J)
-    dw2 = ops.mm_tn(dlog2, hid2, p, dy16=dl16, x16=hid2 if p == "bf16" else None)
+    if p == "bf16" and V % 256 == 0:
+        # compute dW2^T = hidden^T dlogits ([J, V]: 256-wide tcgen05 tiles divide V, not J) and flip it
+        dw2 = ops.mm_tn(hid2, dl16, p, dy16=hid2, x16=dl16).t().contiguous()
+    else:
+        dw2 = ops.mm_tn(dlog2, hid2, p, dy16=dl16, x16=hid2 if p == "bf16" else None)
     dhid = ops.mm_nn(dlog2, w2, p, dy16=dl16, out_bf16=(p == "bf16"))
     dep, ddp = ops.joint_hidden_bwd(dhid.view(B, T, U, J), hid)
     dep2, ddp2 = dep.view(B * T, J), ddp.view(B * U, J)
@@ -266,6 +272,8 @@ class JointLoss(torch.autograd.Function):
         B, T, U, E, Dd, J, V = ctx.dims
         p = ctx.precision
         g = _c(go.to(f32)).view(-1)
+        # (a variant of the gradient kernel that also accumulated the bias gradient in registers was
+        #  measured 2.5x slower -- occupancy -- than this kernel plus a separate column-sum pass)
         if p == "bf16":
             dl = ops.rnnt_loss_bwd(logits, labels, act_lens, label_lens, ctx.blank, ws, g, 1.0 / B, out_bf16=True)
         else:

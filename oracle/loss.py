@@ -27,6 +27,7 @@ def build(quiet=True):
 
 _lib = None
 _ref = None
+NUM_THREADS = 0      # 0 = OpenMP default; bench.py sets this for the reference library (options.num_threads)
 
 
 def _oracle():
@@ -126,7 +127,7 @@ def ref_cpu(log_probs, labels, act_lens, label_lens, blank=0, want_grads=True,
     ws = np.zeros(size.value, dtype=np.uint8)
     costs = np.zeros(B, dtype=dtype)
     grads = np.zeros_like(lp) if want_grads else None
-    opt = RnntOptions(loc=0, num_threads=num_threads, stream=None, blank_label=blank,
+    opt = RnntOptions(loc=0, num_threads=num_threads or NUM_THREADS, stream=None, blank_label=blank,
                       maxT=T, maxU=U, batch_first=True)
     fn = lib.compute_rnnt_loss if dtype == np.float32 else lib.compute_rnnt_loss_fp64
     st = fn(_p(lp), _p(grads) if want_grads else None, _p(labels), _p(label_lens), _p(act_lens),
