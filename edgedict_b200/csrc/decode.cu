@@ -193,6 +193,13 @@ __device__ void phase_argmax(const EbPhase& p) {
             pred = bi;
             if (pred != unk) break;
         }
+        if (p.flags & 8) {                                     // batched greedy (models.py:253-255): accumulate
+            const float best = __ldcg(x + pred);               // log_softmax(x)[pred] = -log sum exp(x - max)
+            float sum = 0.f;
+            for (int v = lane; v < V; v += 32) sum += expf(__ldcg(x + v) - best);
+            sum = warp_sum(sum);
+            if (lane == 0) p.y[s] += -logf(sum);
+        }
         if (lane == 0) {
             p.tok_out[s] = pred;
             if (p.hist) p.hist[(long)s * p.hist_ld + p.hist_col] = pred;

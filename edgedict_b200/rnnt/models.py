@@ -212,28 +212,22 @@ class Transducer(nn.Module):
 
     @torch.no_grad()
     def greedy_decode(self, xs, xlen):
-        """rnnt/models.py:243-269: at most one symbol per encoder frame; returns
-        (list of id arrays incl. blanks, truncated by the UNSCALED xlen as the reference does,
-        -sum log p)."""
+        """rnnt/models.py:243-269: at most one symbol per encoder frame; returns (list of id arrays
+        incl. blanks, truncated by the UNSCALED xlen as the reference does, -sum log p).  The T'
+        per-frame iterations run device-side in one persistent kernel (stream_engine.GreedyEngine)."""
+        from ..stream_engine import GreedyEngine
         h_enc, _ = self.encoder(xs)
-        B = xs.shape[0]
-        h_dec, (h_prev, c_prev) = self.decoder(torch.zeros(B, 0, dtype=torch.long, device=xs.device))
-        y_seq, log_p = [], []
-        for i in range(h_enc.shape[1]):
-            logits = self.joint(h_enc[:, i].contiguous(), h_dec[:, 0].contiguous())
-            probs = torch.log_softmax(logits, dim=1)
-            prob, pred = probs.max(dim=1)
-            y_seq.append(pred)
-            log_p.append(prob)
-            h_new, (h_next, c_next) = self.decoder(pred[:, None], (h_prev, c_prev))
-            keep = (pred != self.blank)
-            h_dec = torch.where(keep[:, None, None], h_new, h_dec)
-            h_prev = torch.where(keep[None, :, None], h_next, h_prev)
-            c_prev = torch.where(keep[None, :, None], c_next, c_prev)
-        y_seq = torch.stack(y_seq, dim=1)
-        log_p = torch.stack(log_p, dim=1).sum(dim=1)
-        out = [seq[:int(n)].cpu().numpy() for seq, n in zip(y_seq, xlen)]
-        return out, -log_p
+        B, T = h_enc.shape[0], h_enc.shape[1]
+        key = (B, T, h_enc.device)
+        cache = self.__dict__.setdefault("_greedy_engines", {})
+        eng = cache.get(key)
+        if eng is None:
+            cache.clear()                                  # one resident program is enough
+            eng = cache[key] = GreedyEngine(self, B, T, blank=self.blank)
+        ids, logp = eng.run(h_enc)
+        ids = ids.cpu().numpy()
+        out = [ids[i, :int(n)].astype("int64") for i, n in enumerate(xlen)]
+        return out, -logp.clone()
 
 
 def _i32(t):

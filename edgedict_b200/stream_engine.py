@@ -16,7 +16,7 @@ from ._lib import lib, check
 from .rnnt.tokenizer import NUL, BOS, UNK
 
 PH_LN, PH_PAIR, PH_LSTM, PH_LINEAR, PH_ARGMAX, PH_COPY = range(6)
-F_TANH, F_EMBED, F_MASKED = 1, 2, 4
+F_TANH, F_EMBED, F_MASKED, F_LOGP = 1, 2, 4, 8
 
 
 class EbPhase(C.Structure):
@@ -160,3 +160,76 @@ class StreamEngine:
         self.xin.copy_(chunk, non_blocking=True)
         self._run(self._chunk, self.n_chunk_phases)
         return self.hist
+
+
+class GreedyEngine:
+    """Device-side batched greedy decode (reference Transducer.greedy_decode, rnnt/models.py:243-269):
+    the T' per-frame iterations (joint -> log_softmax/argmax -> predictor step for every row -> keep
+    the new state only where the prediction is non-blank) run inside ONE cooperative kernel launch as
+    a phase program over the encoder output, instead of T' Python iterations of ~10 launches each."""
+
+    def __init__(self, transducer, batch, t_out, blank=NUL, max_ctas=0):
+        dec, joint = transducer.decoder, transducer.joint.joint
+        self.dev = dec.embed.weight.device
+        f32 = torch.float32
+        B, T = batch, t_out
+        self.B, self.T, self.blank, self.max_ctas = B, T, blank, max_ctas
+        z = lambda *shape: torch.zeros(*shape, dtype=f32, device=self.dev)
+        Ld, Hd = dec.lstm.num_layers, dec.lstm.hidden_size
+        Em, D = dec.embed.weight.shape[1], dec.proj.weight.shape[0]
+        J, V = joint[0].weight.shape[0], joint[2].weight.shape[0]
+        E = joint[0].weight.shape[1] - D
+        self.h_enc = z(B, T, E)
+        self.dec_h, self.dec_c, self.dec_htmp = z(Ld, B, Hd), z(Ld, B, Hd), z(Ld, B, Hd)
+        self.dec_x, self.hidden, self.logits = z(B, D), z(B, J), z(B, V)
+        self.tok = torch.zeros(B, dtype=torch.int32, device=self.dev)
+        self.hist = torch.zeros(B, T, dtype=torch.int32, device=self.dev)
+        self.logp = z(B)
+        self._keep = [p.detach() for p in transducer.parameters()]
+        prog = []
+
+        def ph(**kw):
+            q = EbPhase()
+            for k, v in kw.items():
+                setattr(q, k, v)
+            prog.append(q)
+
+        def predictor(masked):
+            fl = F_EMBED | (F_MASKED if masked else 0)
+            for k in range(Ld):
+                w = [getattr(dec.lstm, n % k) for n in ("weight_ih_l%d", "weight_hh_l%d", "bias_ih_l%d", "bias_hh_l%d")]
+                ph(type=PH_LSTM, S=B, N=Hd, K1=Em if k == 0 else Hd, K2=Hd, flags=fl if k == 0 else (fl & F_MASKED),
+                   x1=_ptr(dec.embed.weight) if k == 0 else _ptr(self.dec_htmp[k - 1]), ldx1=Em if k == 0 else Hd,
+                   x2=_ptr(self.dec_h[k]), ldx2=Hd, w1=_ptr(w[0]), ldw1=w[0].shape[1], w2=_ptr(w[1]), ldw2=Hd,
+                   b1=_ptr(w[2]), b2=_ptr(w[3]), c=_ptr(self.dec_c[k]), y=_ptr(self.dec_htmp[k]), ldy=Hd,
+                   tok_in=_ptr(self.tok), aux=blank)
+            ph(type=PH_COPY, S=Ld * B, N=Hd, x1=_ptr(self.dec_htmp), y=_ptr(self.dec_h))
+            ph(type=PH_LINEAR, S=B, N=D, K1=Hd, x1=_ptr(self.dec_h[Ld - 1]), ldx1=Hd, w1=_ptr(dec.proj.weight), ldw1=Hd,
+               b1=_ptr(dec.proj.bias), y=_ptr(self.dec_x), ldy=D)
+
+        predictor(masked=False)                          # prime with BOS from the zero state
+        w1 = joint[0].weight
+        for k in range(T):
+            ph(type=PH_LINEAR, S=B, N=J, flags=F_TANH, K1=E, x1=_ptr(self.h_enc, k * E), ldx1=T * E, w1=_ptr(w1),
+               ldw1=E + D, K2=D, x2=_ptr(self.dec_x), ldx2=D, w2=_ptr(w1, E), ldw2=E + D, b1=_ptr(joint[0].bias),
+               y=_ptr(self.hidden), ldy=J)
+            ph(type=PH_LINEAR, S=B, N=V, K1=J, x1=_ptr(self.hidden), ldx1=J, w1=_ptr(joint[2].weight), ldw1=J,
+               b1=_ptr(joint[2].bias), y=_ptr(self.logits), ldy=V)
+            ph(type=PH_ARGMAX, S=B, N=V, flags=F_LOGP, x1=_ptr(self.logits), ldx1=V, aux=blank, aux2=-1,
+               tok_out=_ptr(self.tok), hist=_ptr(self.hist), hist_ld=T, hist_col=k, y=_ptr(self.logp))
+            predictor(masked=True)
+        self.nphase = len(prog)
+        arr = (EbPhase * len(prog))(*prog)
+        self._prog = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(self.dev)
+        self._bar = torch.zeros(64, dtype=torch.int32, device=self.dev)
+
+    @torch.no_grad()
+    def run(self, h_enc):
+        """h_enc [B, T', E] -> (ids int32 [B, T'] incl. blanks, sum of log p [B])."""
+        self.h_enc.copy_(h_enc)
+        for t in (self.dec_h, self.dec_c, self.logp):
+            t.zero_()
+        self.tok.fill_(BOS)
+        check(lib().eb_decode_run(self._prog.data_ptr(), self.nphase, self._bar.data_ptr(), self.max_ctas,
+                                  torch.cuda.current_stream().cuda_stream), "eb_decode_run")
+        return self.hist, self.logp

@@ -111,7 +111,8 @@ typedef struct EbPhase {
     int32_t* hist;
 } EbPhase;
 /* flags: 1 = tanh epilogue (LINEAR); 2 = x1 rows are embedding rows indexed by tok_in (LSTM);
- *        4 = masked update: streams whose tok_in equals aux (blank) keep their state (LSTM). */
+ *        4 = masked update: streams whose tok_in equals aux (blank) keep their state (LSTM);
+ *        8 = ARGMAX also accumulates log_softmax(x)[argmax] into y[s] (batched greedy decode). */
 int eb_decode_phase_size(void);
 int eb_decode_run(const void* phases_dev, int nphase, void* barrier_dev, int max_ctas, void* stream);
 
