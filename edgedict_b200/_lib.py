@@ -15,6 +15,9 @@ SIGNATURES = {
     "eb_rnnt_workspace_bytes": (Z, [I, I, I, I]),
     "eb_rnnt_loss_fwd": (I, [P, P, P, P, I, I, I, I, I, I, P, P, I, P]),
     "eb_rnnt_loss_bwd": (I, [P, P, I, P, P, P, I, I, I, I, I, I, P, P, I, D, P]),
+    "eb_rnnt_loss_lattice": (I, [P, P, I, I, I, P, P, I, P]),
+    "eb_rnnt_loss_bwd_bf16": (I, [P, P, P, P, P, I, I, I, I, I, P, P, I, D, P]),
+    "eb_joint_logits_lse": (I, [P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, P]),
     "eb_rnnt_workspace_views": (I, [P, I, I, I, I, P, P, P, P, P]),
     "eb_gemm_f32": (I, [P, L, L, P, L, L, P, L, P, I, I, I, F, F, P]),
     "eb_gemm_bf16": (I, [P, I, P, I, P, I, P, I, L, I, L, P]),

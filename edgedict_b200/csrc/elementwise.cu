@@ -344,6 +344,47 @@ __global__ void colsum_kernel(const TI* __restrict__ x, float* __restrict__ out,
     atomicAdd(out + c, acc);
 }
 
+// bf16 rows with N % 8 == 0: each thread owns 8 consecutive columns (one 16-byte load per row) and
+// keeps four independent row loads in flight; one atomic per column per CTA at the end
+__global__ void colsum_bf16_vec_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, long rows,
+                                       int N, long rows_per_block) {
+    const int c8 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c8 * 8 >= N) return;
+    const long r0 = (long)blockIdx.y * rows_per_block;
+    const long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const __nv_bfloat16* p = x + r0 * N + (long)c8 * 8;
+    long r = r0;
+    for (; r + 3 < r1; r += 4) {
+        uint4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = *reinterpret_cast<const uint4*>(p + (long)k * N);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+                acc[2 * i] += f.x;
+                acc[2 * i + 1] += f.y;
+            }
+        }
+        p += 4L * N;
+    }
+    for (; r < r1; ++r, p += N) {
+        const uint4 v = *reinterpret_cast<const uint4*>(p);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+            acc[2 * i] += f.x;
+            acc[2 * i + 1] += f.y;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) atomicAdd(out + (long)c8 * 8 + i, acc[i]);
+}
+
 __global__ void cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long n) {
     long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const long stride = (long)gridDim.x * blockDim.x * 4;
@@ -529,7 +570,13 @@ EB_API int eb_colsum(const void* x, int x_bf16, float* out, long rows, int N, vo
     long rpb = (rows + 255) / 256;
     if (rpb < 64) rpb = 64;
     dim3 grid((N + 127) / 128, (unsigned)((rows + rpb - 1) / rpb));
-    if (x_bf16)
+    if (x_bf16 && N % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+        long rpb2 = (rows + 1023) / 1024;
+        if (rpb2 < 32) rpb2 = 32;
+        const int nth = (N / 8 < 128) ? N / 8 : 128;
+        dim3 g2((N / 8 + nth - 1) / nth, (unsigned)((rows + rpb2 - 1) / rpb2));
+        colsum_bf16_vec_kernel<<<g2, nth, 0, ST(stream)>>>((const __nv_bfloat16*)x, out, rows, N, rpb2);
+    } else if (x_bf16)
         colsum_kernel<__nv_bfloat16><<<grid, 128, 0, ST(stream)>>>((const __nv_bfloat16*)x, out, rows, N, rpb);
     else
         colsum_kernel<float><<<grid, 128, 0, ST(stream)>>>((const float*)x, out, rows, N, rpb);

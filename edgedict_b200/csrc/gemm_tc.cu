@@ -24,17 +24,22 @@ namespace {
 
 constexpr int BM = 128, BK = 64, UMMA_K = 16;
 constexpr int A_BYTES = BM * BK * 2;
-constexpr int EPI_BYTES = 4 * 32 * 36 * 4;
-constexpr int NTHREADS = 192;
+constexpr int EPI_WARP_BYTES = 32 * 36 * 4;
 // Tile width BN_ = 128 (5 stages, 2 x 128 TMEM columns) or 256 (4 stages, 2 x 256 = all 512 TMEM
 // columns).  A 128 x 128 x 16 MMA reads 8 KB of shared memory in 64 cycles = the 128 B/clk limit of
 // the SM; the 128 x 256 tile reads 12 KB in 128 cycles, which leaves headroom for the TMA writes.
-template <int BN_> struct Cfg {
+// EPW_ = epilogue warps: 4 (one per TMEM lane quadrant) or 8 (two per quadrant, alternating 32-column
+// chunks).  The epilogue of a short-K GEMM is latency-bound with a single warp per scheduler; with 8 warps
+// two of them interleave on every scheduler.  The wide tile then keeps 3 instead of 4 smem stages.
+template <int BN_, int EPW_ = 4> struct Cfg {
     static constexpr int BN = BN_;
-    static constexpr int STAGES = BN_ == 256 ? 4 : 5;
+    static constexpr int EPW = EPW_;
+    static constexpr int NTHREADS = 64 + 32 * EPW_;
+    static constexpr int STAGES = BN_ == 256 ? (EPW_ == 8 ? 3 : 4) : 5;
     static constexpr int B_BYTES = BN_ * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int TMEM_COLS = 2 * BN_;
+    static constexpr int EPI_BYTES = EPW_ * EPI_WARP_BYTES;
     static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + EPI_BYTES + 256;
 };
 
@@ -129,16 +134,27 @@ struct Sched {
     }
 };
 
+// Optional fused epilogue of the joint's output GEMM (rows = lattice cells (b,t,u), columns = vocabulary):
+// while the logits tile leaves TMEM, each epilogue thread owns one row and keeps an online
+// (max, sum-exp) over the whole vocabulary across the consecutive column tiles of its row block, plus
+// the blank and label logits -- i.e. everything rnnt_denom_kernel would otherwise re-read 8 GB for.
+struct LseArgs {
+    const int* labels; const int* xlen; const int* ylen;     // [B,maxU-1], [B], [B]
+    float* denom; float* lpb; float* lpl;                     // [B*maxT*maxU] each (loss workspace)
+    int maxT, maxU, blank;
+};
+
 // A_MN / B_MN: operand stored with its M (resp. N) index contiguous ("MN-major"), else K contiguous.
 //   K-major tile in smem : [128 rows][64 k] bf16, 128 B per row, 128B swizzle; SBO = 1024 (8 rows)
 //   MN-major tile in smem: 2 x [64 k][64 mn] bf16, 128 B per k-row; SBO = 1024 (8 k-rows), LBO = 8192
-template <bool A_MN, bool B_MN, int BN_>
-__global__ void __launch_bounds__(NTHREADS, 1)
+template <bool A_MN, bool B_MN, int BN_, bool LSE = false, int EPW_ = 4>
+__global__ void __launch_bounds__(64 + 32 * EPW_, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                void* __restrict__ Cout, int c_bf16, const float* __restrict__ bias, int accumulate,
-               long M, int N, long K, int ksplit) {
-    constexpr int BN = BN_, STAGES = Cfg<BN_>::STAGES, STAGE_BYTES = Cfg<BN_>::STAGE_BYTES;
-    constexpr int TMEM_COLS = Cfg<BN_>::TMEM_COLS;
+               long M, int N, long K, int ksplit, LseArgs lse = LseArgs()) {
+    using C_ = Cfg<BN_, EPW_>;
+    constexpr int BN = BN_, STAGES = C_::STAGES, STAGE_BYTES = C_::STAGE_BYTES;
+    constexpr int TMEM_COLS = C_::TMEM_COLS, EPI_BYTES = C_::EPI_BYTES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* tiles = smem;
@@ -154,13 +170,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const int num_n = (N + BN - 1) / BN;
     Sched sch;
     sch.num_m = num_m; sch.num_n = num_n; sch.ksplit = ksplit; sch.out_tiles = num_m * num_n;
-    sch.n_inner = (ksplit == 1) && (num_m >= 2L * gridDim.x);
+    sch.n_inner = LSE || ((ksplit == 1) && (num_m >= 2L * gridDim.x));   // LSE needs a row block's tiles back to back
     const int nkb_total = (int)((K + BK - 1) / BK);
     const int kb_per = (nkb_total + ksplit - 1) / ksplit;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, EPW_); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tma_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tma_b) : "memory");
@@ -233,7 +249,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const int q = warp & 3;                             // TMEM lane quadrant this warp may read
         // per-warp staging tile [32 rows][36 floats] (16-byte aligned rows: conflict-free 128-bit
         // writes by row and 128-bit reads by 8-lane row groups), addressed in the shared window
-        const uint32_t sbuf = smem_u32(epi) + (uint32_t)(warp - 2) * (32 * 36 * 4);
+        const uint32_t sbuf = smem_u32(epi) + (uint32_t)(warp - 2) * EPI_WARP_BYTES;
+        const int chalf = (warp - 2) >> 2;                    // EPW == 8: which chunks (even / odd) this warp drains
         const int rsub = lane >> 3, c4 = lane & 7;          // read-back mapping: 4 rows x 8 float4 per pass
         float* const Cf = reinterpret_cast<float*>(Cout);
         __nv_bfloat16* const Ch = reinterpret_cast<__nv_bfloat16*>(Cout);
@@ -241,30 +258,76 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const bool bias_vec = (reinterpret_cast<uintptr_t>(bias) & 15) == 0;
         long it = 0;
         long mb; int nb, ks;
+        float rm = -INFINITY, rs = 0.f, xb = 0.f, xl = 0.f;     // LSE: running row statistics
+        int lab = -1; bool cell_ok = false;
         for (long jj = 0; sch.get(jj, mb, nb, ks); ++jj, ++it) {
             const bool empty_split = ks * kb_per >= nkb_total;      // (only when K is tiny) nothing accumulated
             const uint32_t acc = (uint32_t)(it & 1), acc_phase = (uint32_t)((it >> 1) & 1);
             const long m0 = mb * BM;
             const int n0 = nb * BN;
             const bool full = vec_ok && (m0 + BM <= M) && (n0 + BN <= N);
+            if (LSE && nb == 0) {                                 // new row block: reset, decode (b,t,u) of my row
+                rm = -INFINITY; rs = 0.f; xb = 0.f; xl = 0.f; lab = -1; cell_ok = false;
+                const long cell = m0 + q * 32 + lane;
+                if (cell < M) {
+                    const int u = (int)(cell % lse.maxU);
+                    const long bt = cell / lse.maxU;
+                    const int t = (int)(bt % lse.maxT), b = (int)(bt / lse.maxT);
+                    const int Tn = lse.xlen[b], Un = lse.ylen[b] + 1;
+                    cell_ok = t < Tn && u < Un;
+                    if (cell_ok && u < Un - 1) lab = lse.labels[b * (lse.maxU - 1) + u];
+                }
+            }
             mbar_wait(tfull0 + 8 * acc, acc_phase);
             tc_fence_after();
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = (EPW_ == 8 ? chalf : 0); c < BN / 32; c += (EPW_ == 8 ? 2 : 1)) {
                 uint32_t r[32];
                 tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c * 32, r);
                 if (empty_split) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) r[i] = 0u;
                 }
+                if (LSE) {      // add the bias here (the statistics are over logits = acc + b2), then online softmax
+                    const int col0 = n0 + c * 32;
+                    float cm = -INFINITY;
+#pragma unroll
+                    for (int i4 = 0; i4 < 8; ++i4) {
+                        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (bias) {
+                            if (col0 + i4 * 4 + 3 < N) b4 = __ldg(reinterpret_cast<const float4*>(bias + col0 + i4 * 4));
+                        }
+                        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            float v = __uint_as_float(r[i4 * 4 + e]) + bb[e];
+                            if (col0 + i4 * 4 + e >= N) v = -INFINITY;
+                            r[i4 * 4 + e] = __float_as_uint(v);
+                            cm = fmaxf(cm, v);
+                        }
+                    }
+                    const float nm = fmaxf(rm, cm);
+                    float a = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) a += __expf(__uint_as_float(r[i]) - nm);
+                    rs = rs * __expf(rm - nm) + a;
+                    rm = nm;
+                }
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
                     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" :: "r"(sbuf + (uint32_t)(lane * 36 + i * 4) * 4),
                                  "r"(r[4 * i]), "r"(r[4 * i + 1]), "r"(r[4 * i + 2]), "r"(r[4 * i + 3]) : "memory");
                 __syncwarp();
+                if (LSE) {
+                    const int col0 = n0 + c * 32;
+                    if (lse.blank >= col0 && lse.blank < col0 + 32)
+                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(xb) : "r"(sbuf + (uint32_t)(lane * 36 + lse.blank - col0) * 4) : "memory");
+                    if (lab >= col0 && lab < col0 + 32)
+                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(xl) : "r"(sbuf + (uint32_t)(lane * 36 + lab - col0) * 4) : "memory");
+                }
                 const int col = n0 + c * 32 + c4 * 4;
                 float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (bias && ks == 0) {
+                if (bias && ks == 0 && !LSE) {
                     if (full && bias_vec) bv = *reinterpret_cast<const float4*>(bias + col);
                     else {
                         bv.x = col < N ? bias[col] : 0.f; bv.y = col + 1 < N ? bias[col + 1] : 0.f;
@@ -272,11 +335,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     }
                 }
                 const long row0 = m0 + q * 32 + rsub;
+                // all eight 128-bit reads of this lane are issued before anything consumes them (one warp per
+                // scheduler: back-to-back LDS -> FADD -> STG chains would expose the full LDS latency 8 times)
+                float4 vv[8];
+#pragma unroll
+                for (int rr = 0; rr < 8; ++rr)
+                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                                 : "=f"(vv[rr].x), "=f"(vv[rr].y), "=f"(vv[rr].z), "=f"(vv[rr].w)
+                                 : "r"(sbuf + (uint32_t)((rr * 4 + rsub) * 36 + c4 * 4) * 4));
 #pragma unroll
                 for (int rr = 0; rr < 8; ++rr) {
-                    float4 v;
-                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                                 : "r"(sbuf + (uint32_t)((rr * 4 + rsub) * 36 + c4 * 4) * 4) : "memory");
+                    float4 v = vv[rr];
                     v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
                     const long row = row0 + rr * 4;
                     if (full) {
@@ -324,6 +393,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     }
                 }
                 __syncwarp();
+            }
+            if (LSE && nb == num_n - 1 && cell_ok) {              // whole vocabulary seen: publish the row statistics
+                const long cell = m0 + q * 32 + lane;
+                const float d = -(rm + logf(rs));
+                lse.denom[cell] = d;
+                lse.lpb[cell] = d + xb;
+                lse.lpl[cell] = d + xl;
             }
             tc_fence_before();
             if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
@@ -385,20 +461,78 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, void* C, int c_bf16, co
         if (ksplit < 1) ksplit = 1;
     }
     if (ksplit > 1 && !accumulate) EB_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, st));
-    auto kern = gemm_tc_kernel<A_MN, B_MN, BN_>;
+    const long tiles = out_tiles * ksplit;
+    const int grid = (int)(tiles < eb_num_sms() ? tiles : eb_num_sms());
+    // short contraction per tile => the epilogue, not the MMA, paces the tile: use 8 epilogue warps
+    static int force_epw = -1;
+    if (force_epw < 0) { const char* e = getenv("EDGEDICT_GEMM_EPW"); force_epw = e ? atoi(e) : 0; }
+    const bool epi8 = force_epw ? (force_epw == 8) : ((K + ksplit - 1) / ksplit <= 2048);
+    if (epi8) {
+        auto kern = gemm_tc_kernel<A_MN, B_MN, BN_, false, 8>;
+        static bool attr_done = false;
+        if (!attr_done) {
+            EB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN_, 8>::SMEM_BYTES));
+            attr_done = true;
+        }
+        kern<<<grid, Cfg<BN_, 8>::NTHREADS, Cfg<BN_, 8>::SMEM_BYTES, st>>>(ta, tb, C, c_bf16, bias, accumulate, M, N, K, ksplit, LseArgs());
+    } else {
+        auto kern = gemm_tc_kernel<A_MN, B_MN, BN_, false, 4>;
+        static bool attr_done = false;
+        if (!attr_done) {
+            EB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN_, 4>::SMEM_BYTES));
+            attr_done = true;
+        }
+        kern<<<grid, Cfg<BN_, 4>::NTHREADS, Cfg<BN_, 4>::SMEM_BYTES, st>>>(ta, tb, C, c_bf16, bias, accumulate, M, N, K, ksplit, LseArgs());
+    }
+    EB_CHECK_LAUNCH();
+    return EB_OK;
+}
+
+template <int BN_>
+int launch_lse(const CUtensorMap& ta, const CUtensorMap& tb, void* C, const float* bias, long M, int N, long K,
+               const LseArgs& lse, cudaStream_t st) {
+    auto kern = gemm_tc_kernel<false, false, BN_, true>;
     static bool attr_done = false;
     if (!attr_done) {
         EB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN_>::SMEM_BYTES));
         attr_done = true;
     }
-    const long tiles = out_tiles * ksplit;
-    const int grid = (int)(tiles < eb_num_sms() ? tiles : eb_num_sms());
-    kern<<<grid, NTHREADS, Cfg<BN_>::SMEM_BYTES, st>>>(ta, tb, C, c_bf16, bias, accumulate, M, N, K, ksplit);
+    const long num_m = (M + BM - 1) / BM;
+    const int grid = (int)(num_m < eb_num_sms() ? num_m : eb_num_sms());
+    kern<<<grid, Cfg<BN_>::NTHREADS, Cfg<BN_>::SMEM_BYTES, st>>>(ta, tb, C, 1, bias, 0, M, N, K, 1, lse);
     EB_CHECK_LAUNCH();
     return EB_OK;
 }
 
 }  // namespace
+
+// Joint output layer fused with the softmax statistics of the RNN-T loss (bf16 mode):
+//   logits16[cell, v] = bf16(hidden16[cell, :] . W2_16[v, :] + b2[v]),  cell = (b*maxT + t)*maxU + u
+//   denom[cell] = -logsumexp_v(logits fp32),  lpb/lpl[cell] = log p(blank), log p(label[u])   (valid cells only)
+// replaces Joint's second Linear (rnnt/models.py:165) + reduce_max/reduce_exp (reduce.h:45-104) + the
+// gathers of compute_alphas/betas (gpu_rnnt_kernel.h:5-9) without re-reading the logits.
+EB_API int eb_joint_logits_lse(const void* hidden16, const void* w2_16, const float* b2, void* logits16,
+                               const int* labels, const int* xlen, const int* ylen, float* denom, float* lpb,
+                               float* lpl, int B, int maxT, int maxU, int V, int J, int blank, void* stream) {
+    if (!hidden16 || !w2_16 || !logits16 || !xlen || !ylen || !denom || !lpb || !lpl || (!labels && maxU > 1) ||
+        B <= 0 || maxT <= 0 || maxU <= 0 || V <= 0 || J <= 0 || J % 8 || blank < 0 || blank >= V)
+        return EB_ERR_INVALID;
+    if ((reinterpret_cast<uintptr_t>(hidden16) & 15) || (reinterpret_cast<uintptr_t>(w2_16) & 15) ||
+        (b2 && (reinterpret_cast<uintptr_t>(b2) & 15)))
+        return EB_ERR_INVALID;
+    const long M = (long)B * maxT * maxU;
+    const bool wide = (V % 256 == 0);
+    CUtensorMap ta, tb;
+    if (!make_map(&ta, hidden16, (uint64_t)J, (uint64_t)M, 128) || !make_map(&tb, w2_16, (uint64_t)J, (uint64_t)V, wide ? 256 : 128)) {
+        fprintf(stderr, "[edgedict_b200] cuTensorMapEncodeTiled failed\n");
+        return EB_ERR_CUDA;
+    }
+    LseArgs lse;
+    lse.labels = labels; lse.xlen = xlen; lse.ylen = ylen; lse.denom = denom; lse.lpb = lpb; lse.lpl = lpl;
+    lse.maxT = maxT; lse.maxU = maxU; lse.blank = blank;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    return wide ? launch_lse<256>(ta, tb, logits16, b2, M, V, J, lse, st) : launch_lse<128>(ta, tb, logits16, b2, M, V, J, lse, st);
+}
 
 EB_API int eb_gemm_bf16(const void* A, int a_mn_major, const void* B, int b_mn_major, void* C, int c_bf16,
                         const float* bias, int accumulate, long M, int N, long K, void* stream) {

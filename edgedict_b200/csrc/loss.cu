@@ -66,6 +66,21 @@ template <typename T, bool VEC> struct Row4 {
     }
 };
 
+// bf16 logits (written by the fused joint GEMM epilogue): 4 values per 8-byte load
+template <bool VEC> struct Row4<__nv_bfloat16, VEC> {
+    static __device__ __forceinline__ void load(const __nv_bfloat16* row, int v, int V, float (&x)[4]) {
+        if (VEC) {
+            const uint2 q = *reinterpret_cast<const uint2*>(row + v);
+            const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q.x));
+            const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q.y));
+            x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) x[i] = (v + i < V) ? __bfloat162float(row[v + i]) : -INFINITY;
+        }
+    }
+};
+
 // ---------------------------------------------------------------------------------------------
 // 1. denominators + (blank, label) gather
 // ---------------------------------------------------------------------------------------------
@@ -257,9 +272,9 @@ template <> struct Store4<__nv_bfloat16> {
     }
 };
 
-template <typename T, typename TO, bool VEC, int WARPS>
+template <typename T, typename TO, bool VEC, int WARPS, typename TI = T>
 __global__ void __launch_bounds__(WARPS * 32)
-rnnt_grad_kernel(const T* logits, TO* grads, const int* __restrict__ labels,
+rnnt_grad_kernel(const TI* logits, TO* grads, const int* __restrict__ labels,
                  const int* __restrict__ xlen, const int* __restrict__ ylen,
                  const T* __restrict__ denom, const T* __restrict__ alphas,
                  const T* __restrict__ betas, const T* __restrict__ ll_fwd,
@@ -274,7 +289,7 @@ rnnt_grad_kernel(const T* logits, TO* grads, const int* __restrict__ labels,
         const int t = (int)(bt % maxT);
         const int b = (int)(bt / maxT);
         const int Tn = xlen[b], Un = ylen[b] + 1;
-        const T* row = logits + cell * (long)V;
+        const TI* row = logits + cell * (long)V;
         TO* orow = grads + cell * (long)V;
         if (t >= Tn || u >= Un) {                         // padded: zero, logits never read
             for (int v = lane * 4; v < V; v += 128) {
@@ -298,7 +313,7 @@ rnnt_grad_kernel(const T* logits, TO* grads, const int* __restrict__ labels,
         const T c_lab = (lab >= 0) ? a - ll + d + betas[cell + 1] : M<T>::ninf();
         for (int v = lane * 4; v < V; v += 128) {
             T x[4];
-            Row4<T, VEC>::load(row, v, V, x);
+            Row4<TI, VEC>::load(row, v, V, x);
             T g[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -518,6 +533,46 @@ EB_API int eb_rnnt_loss_bwd(const void* logits, void* grads, int grads_bf16, con
                                         maxT, maxU, V, blank, workspace, (const double*)gscale_dev,
                                         gscale_per_batch, host_scale, st);
     return EB_ERR_INVALID;
+}
+
+// Lattice only: denom / lpb / lpl of the workspace were already produced by eb_joint_logits_lse.
+EB_API int eb_rnnt_loss_lattice(const int* xlen, const int* ylen, int B, int maxT, int maxU, void* workspace,
+                                float* costs_dev, int need_beta, void* stream) {
+    if (!xlen || !ylen || !workspace || B <= 0 || maxT <= 0 || maxU <= 0 || maxU > 1024) return EB_ERR_INVALID;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    Workspace<float> w(workspace, B, maxT, maxU);
+    const int threads = ((maxU + 31) / 32) * 32;
+    rnnt_lattice_kernel<float, 8><<<dim3(B, 2), threads, 2 * threads * sizeof(float), st>>>(
+        w.lpb, w.lpl, xlen, ylen, w.alphas, w.betas, w.ll_fwd, w.ll_bwd, maxT, maxU, need_beta);
+    EB_CHECK_LAUNCH();
+    if (costs_dev) neg_copy_kernel<float><<<(B + 127) / 128, 128, 0, st>>>(w.ll_fwd, costs_dev, B);
+    EB_CHECK_LAUNCH();
+    return EB_OK;
+}
+
+// Gradient wrt bf16 logits, written as bf16 (grads16 may alias logits16: in place).
+EB_API int eb_rnnt_loss_bwd_bf16(const void* logits16, void* grads16, const int* labels, const int* xlen,
+                                 const int* ylen, int B, int maxT, int maxU, int V, int blank, void* workspace,
+                                 const float* gscale_dev, int gscale_per_batch, double host_scale, void* stream) {
+    if (!logits16 || !grads16 || !workspace) return EB_ERR_INVALID;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    Workspace<float> w(workspace, B, maxT, maxU);
+    const long ncells = (long)B * maxT * maxU;
+    constexpr int WARPS = 8;
+    const bool vec = (V % 4 == 0) && ((reinterpret_cast<uintptr_t>(logits16) & 7) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(grads16) & 7) == 0);
+    const __nv_bfloat16* in = reinterpret_cast<const __nv_bfloat16*>(logits16);
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(grads16);
+    if (vec)
+        rnnt_grad_kernel<float, __nv_bfloat16, true, WARPS, __nv_bfloat16><<<row_grid(ncells, WARPS), WARPS * 32, 0, st>>>(
+            in, out, labels, xlen, ylen, w.denom, w.alphas, w.betas, w.ll_fwd, gscale_dev, gscale_per_batch,
+            (float)host_scale, B, maxT, maxU, V, blank);
+    else
+        rnnt_grad_kernel<float, __nv_bfloat16, false, WARPS, __nv_bfloat16><<<row_grid(ncells, WARPS), WARPS * 32, 0, st>>>(
+            in, out, labels, xlen, ylen, w.denom, w.alphas, w.betas, w.ll_fwd, gscale_dev, gscale_per_batch,
+            (float)host_scale, B, maxT, maxU, V, blank);
+    EB_CHECK_LAUNCH();
+    return EB_OK;
 }
 
 // debugging / test access to the lattice (device pointers into the workspace)

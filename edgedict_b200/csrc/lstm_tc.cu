@@ -88,31 +88,11 @@ __device__ __forceinline__ void warp_pull(__nv_bfloat16* dst, int dst_ld, const 
     __syncwarp();
 }
 
-// ---- dataflow synchronisation: ONE FLAG PER PRODUCER CTA, no atomics -----------------------------
-// A CTA publishes its slice of the exchange buffer and then stores its own monotonically increasing
-// flag with release semantics; a consumer warp needs only the producers of its own K-range, and
-// polls their (contiguous) flags with one lane per producer -- one coalesced request per poll.
-__device__ __forceinline__ void flag_release(unsigned* flag, unsigned value) {
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(flag), "r"(value) : "memory");
-}
-// lanes [0, n) each wait until flags[first + lane] >= target (n <= 32)
-__device__ __forceinline__ void flags_wait(const unsigned* flags, int first, int n, unsigned target) {
-    const int l = threadIdx.x & 31;
-    if (l < n) spin_wait_ge(flags + first + l, target);
-    __syncwarp();
-}
-// legacy counter barrier (per-group reduce of the non-cluster BPTT variant)
-__device__ __forceinline__ void warp_wait(const unsigned* ctr, unsigned target) {
-    if ((threadIdx.x & 31) == 0) spin_wait_ge(ctr, target);
-    __syncwarp();
-}
-__device__ __forceinline__ void warp_release(unsigned* ctr) {
-    __syncwarp();
-    if ((threadIdx.x & 31) == 0) {
-        __threadfence();
-        atomicAdd(ctr, 1u);
-    }
-}
+// Grid barrier = monotonic counter: every CTA adds 1 after publishing (one thread: fence + atomic),
+// ONE thread per CTA polls with ld.acquire.gpu, then a block barrier.  Alternatives that were
+// measured and rejected (profiles/r1/lstm_fwd_sync_experiments.txt): a poller per warp (+1.1 us per
+// step of contention on the counter line), one flag per producer with st.release and vector polls
+// (+2..6 us), fence.acq_rel / red.release instead of __threadfence (no change).
 // B fragments for one k-step and all four batch n-tiles out of a padded [NB][ld] bf16 tile
 template <int NT>
 __device__ __forceinline__ void load_b(uint32_t (&b01)[4], uint32_t (&b23)[4], const __nv_bfloat16* tile, int ld,
@@ -223,7 +203,7 @@ __global__ void __launch_bounds__(NW * 32, (NBT == 16) ? 2 : 1) lstm_tc_fwd_kern
             __syncthreads();
         }
         // pull this warp's K-range of h_{t-1}: NB rows x (myks*16) bf16
-        if (!(p.dbg & 2)) warp_pull(hs + ks0 * 16, HP, hprev + ks0 * 16, H, myks * 2, NBT);
+        if (!(p.dbg & 2)) warp_pull(hs + ks0 * 16, HP, hprev + ks0 * 16, H, myks * 2, (p.dbg & 2048) ? NBT / 4 : NBT);
         float acc[2][NT][4];
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)

@@ -8,7 +8,14 @@ import torch
 
 from . import ops
 
+import os
+
 f32, bf16 = torch.float32, torch.bfloat16
+# bf16 mode option: fuse the softmax statistics of the loss into the joint's output GEMM epilogue and keep
+# bf16 logits (EDGEDICT_FUSE_LSE=1).  Correct (tests/test_gpu_model.py) but measured SLOWER on B200
+# (9.6 ms vs 7.5 ms for joint+loss at E6D2): the one-warp-per-scheduler epilogue becomes the bottleneck of the
+# GEMM and the 8-byte-per-lane bf16 gradient pass streams at 3.4 TB/s instead of 5.5 -- off by default.
+FUSE_JOINT_LSE = os.environ.get("EDGEDICT_FUSE_LSE", "0") == "1"
 
 
 def _c(t):
@@ -257,8 +264,17 @@ class JointLoss(torch.autograd.Function):
         he2, hd2, ep, dp = _joint_pre(h_enc, h_dec, w1, b1, precision)
         hid = ops.joint_hidden_fwd(ep, dp, precision == "bf16")
         hid2 = hid.view(B * T * U, J)
-        logits = ops.mm_nt(hid2, w2, b2, precision, x16=hid2 if precision == "bf16" else None).view(B, T, U, V)
-        costs, ws = ops.rnnt_loss_fwd(logits, labels, act_lens, label_lens, blank, need_beta=True)
+        fused = precision == "bf16" and FUSE_JOINT_LSE and J % 8 == 0 and U <= 1024
+        if fused:
+            # bf16 mode: the logits GEMM epilogue also produces the softmax statistics (fp32, from the
+            # TMEM accumulators) and writes bf16 logits; the denominator pass over 8 GB disappears
+            b2a = b2 if (b2.is_contiguous() and b2.data_ptr() % 16 == 0) else b2.clone()
+            logits, ws = ops.joint_logits_lse(hid2, ops.cast_bf16(w2.contiguous()), b2a, labels, act_lens,
+                                              label_lens, B, T, U, blank)
+            costs = ops.rnnt_lattice(act_lens, label_lens, B, T, U, ws)
+        else:
+            logits = ops.mm_nt(hid2, w2, b2, precision, x16=hid2 if precision == "bf16" else None).view(B, T, U, V)
+            costs, ws = ops.rnnt_loss_fwd(logits, labels, act_lens, label_lens, blank, need_beta=True)
         ctx.save_for_backward(hid, he2, hd2, w1, w2, logits, labels, act_lens, label_lens, ws)
         ctx.precision, ctx.dims, ctx.blank = precision, (B, T, U, E, Dd, J, V), blank
         ctx.mark_non_differentiable(costs)
@@ -274,7 +290,9 @@ class JointLoss(torch.autograd.Function):
         g = _c(go.to(f32)).view(-1)
         # (a variant of the gradient kernel that also accumulated the bias gradient in registers was
         #  measured 2.5x slower -- occupancy -- than this kernel plus a separate column-sum pass)
-        if p == "bf16":
+        if logits.dtype == bf16:
+            dl = ops.rnnt_loss_bwd_bf16(logits, labels, act_lens, label_lens, ctx.blank, ws, g, 1.0 / B)
+        elif p == "bf16":
             dl = ops.rnnt_loss_bwd(logits, labels, act_lens, label_lens, ctx.blank, ws, g, 1.0 / B, out_bf16=True)
         else:
             dl = ops.rnnt_loss_bwd(logits, labels, act_lens, label_lens, ctx.blank, ws, g, 1.0 / B, out=logits)

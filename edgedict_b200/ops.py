@@ -356,6 +356,39 @@ def rnnt_loss_bwd(logits, labels, xlen, ylen, blank, ws, gscale, host_scale, out
     return out
 
 
+def joint_logits_lse(hid16, w2_16, b2, labels, xlen, ylen, B, T, U, blank):
+    """bf16 logits [B,T,U,V] + loss workspace with denom / log p(blank) / log p(label) filled in."""
+    V, J = w2_16.shape
+    logits16 = torch.empty(B, T, U, V, dtype=bf16, device=hid16.device)
+    ws = rnnt_workspace(B, T, U, f32, hid16.device)
+    n = B * T * U
+    wsf = ws.view(f32)
+    N = float(n) * V
+    with _timed("joint_logits_lse", 1, 2.0 * n * J + 2.0 * N, 2.0 * N * J):
+        check(lib().eb_joint_logits_lse(_p(hid16), _p(w2_16), _p(b2), _p(logits16), _p(labels), _p(xlen), _p(ylen),
+                                        _p(wsf[0:n]), _p(wsf[n:2 * n]), _p(wsf[2 * n:3 * n]), B, T, U, V, J, blank,
+                                        _s()), "eb_joint_logits_lse")
+    return logits16, ws
+
+
+def rnnt_lattice(xlen, ylen, B, T, U, ws, need_beta=True):
+    costs = torch.empty(B, dtype=f32, device=ws.device)
+    with _timed("rnnt_loss_fwd", 2, 0.0, 0.0):
+        check(lib().eb_rnnt_loss_lattice(_p(xlen), _p(ylen), B, T, U, _p(ws), _p(costs), int(need_beta), _s()),
+              "eb_rnnt_loss_lattice")
+    return costs
+
+
+def rnnt_loss_bwd_bf16(logits16, labels, xlen, ylen, blank, ws, gscale, host_scale):
+    """In place: logits16 becomes d loss / d logits (bf16)."""
+    B, T, U, V = logits16.shape
+    per_batch = int(gscale is not None and gscale.numel() > 1)
+    with _timed("rnnt_loss_bwd", 1, 4.0 * B * T * U * V, 0.0):
+        check(lib().eb_rnnt_loss_bwd_bf16(_p(logits16), _p(logits16), _p(labels), _p(xlen), _p(ylen), B, T, U, V, blank,
+                                          _p(ws), _p(gscale), per_batch, float(host_scale), _s()), "eb_rnnt_loss_bwd_bf16")
+    return logits16
+
+
 def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
     check(lib().eb_adam_step(_p(p), _p(g), _p(m), _p(v), p.numel(), lr, beta1, beta2, eps, weight_decay, step,
                              grad_scale, _s()), "eb_adam_step")

@@ -31,6 +31,13 @@ int eb_rnnt_loss_bwd(const void* logits, void* grads, int grads_bf16, const int*
                      const int* xlen, const int* ylen, int B, int maxT, int maxU, int V, int blank,
                      int dtype_size, void* workspace, const void* gscale_dev /* [1]|[B]|NULL */,
                      int gscale_per_batch, double host_scale, void* stream);
+/* bf16-mode fused path: the joint's output GEMM writes bf16 logits AND the softmax statistics
+ * (eb_joint_logits_lse below), then only the lattice runs, and the gradient is taken on bf16 logits. */
+int eb_rnnt_loss_lattice(const int* xlen, const int* ylen, int B, int maxT, int maxU, void* workspace,
+                         float* costs_dev, int need_beta, void* stream);
+int eb_rnnt_loss_bwd_bf16(const void* logits16, void* grads16, const int* labels, const int* xlen, const int* ylen,
+                          int B, int maxT, int maxU, int V, int blank, void* workspace, const float* gscale_dev,
+                          int gscale_per_batch, double host_scale, void* stream);
 int eb_rnnt_workspace_views(void* workspace, int B, int maxT, int maxU, int dtype_size,
                             void** denom, void** alphas, void** betas, void** ll_fwd, void** ll_bwd);
 
@@ -48,6 +55,13 @@ int eb_gemm_f32(const float* A, long sam, long sak, const float* B, long sbk, lo
  * C = A*B (+ bias[n]) (+ C when accumulate).  Pointers 16-byte aligned, contiguous dim % 8 == 0. */
 int eb_gemm_bf16(const void* A, int a_mn_major, const void* B, int b_mn_major, void* C, int c_bf16,
                  const float* bias, int accumulate, long M, int N, long K, void* stream);
+
+/* joint output layer + softmax statistics in one GEMM (bf16 mode): replaces the second Linear of Joint
+ * (rnnt/models.py:165) together with reduce_max/reduce_exp (warp-transducer reduce.h:45-104) and the
+ * blank/label gathers of the lattice kernels.  denom/lpb/lpl: the first three arrays of the loss workspace. */
+int eb_joint_logits_lse(const void* hidden16, const void* w2_16, const float* b2, void* logits16, const int* labels,
+                        const int* xlen, const int* ylen, float* denom, float* lpb, float* lpl, int B, int maxT,
+                        int maxU, int V, int J, int blank, void* stream);
 
 /* ---- LSTM layer, recurrent part (persistent kernel) ---------------------------------------
  * replaces the time loop of nn.LSTM (rnnt/models.py:45-46,64-65,145-147,154-155).

@@ -156,3 +156,31 @@ def test_bf16_mode_close_to_fp32_mode():
         m.set_precision("fp32")
         l_ac = m(xs, ys, xlen, ylen)                    # autocast selects the bf16 engine
     assert abs(float(l_ac.detach()) - float(l16.detach())) < 1e-6 * abs(float(l16.detach())) + 1e-6
+
+
+@pytest.mark.parametrize("B,T,U,E,D,J,V", [(2, 40, 9, 32, 24, 64, 1024), (3, 17, 5, 16, 16, 56, 64), (2, 130, 3, 40, 24, 72, 256)])
+def test_fused_joint_lse_path_matches_unfused_bf16_path(B, T, U, E, D, J, V):
+    """bf16 mode: the logits GEMM whose epilogue also emits the softmax statistics (+ bf16 logits, in-place
+    bf16 gradient) against the unfused bf16 path (fp32 logits, separate denominator kernel)."""
+    from edgedict_b200 import functional as Fn
+    g = torch.Generator().manual_seed(B * 100 + T)
+    h_enc, h_dec = torch.randn(B, T, E, generator=g), torch.randn(B, U, D, generator=g)
+    w1, b1 = torch.randn(J, E + D, generator=g) / 6, torch.randn(J, generator=g) / 6
+    w2, b2 = torch.randn(V, J, generator=g) / 6, torch.randn(V, generator=g) / 6
+    labels = torch.randint(1, V, (B, U - 1), generator=g, dtype=torch.int32)
+    xl = torch.full((B,), T, dtype=torch.int32)
+    yl = torch.full((B,), U - 1, dtype=torch.int32)
+    if B > 1:
+        xl[1], yl[1] = max(1, T - 7), max(0, U - 3)
+    res = []
+    for fused in (False, True):
+        Fn.FUSE_JOINT_LSE = fused
+        ins = [t.clone().cuda().requires_grad_(True) for t in (h_enc, h_dec, w1, b1, w2, b2)]
+        loss, costs = Fn.JointLoss.apply(*ins, labels.cuda(), xl.cuda(), yl.cuda(), 0, "bf16")
+        loss.backward()
+        res.append((loss.detach().cpu(), costs.cpu(), [t.grad.cpu() for t in ins]))
+    Fn.FUSE_JOINT_LSE = False
+    (l0, c0, g0), (l1, c1, g1) = res
+    assert rel_err(c1, c0) < 2e-3           # same bf16 operands; statistics from fp32 accumulators on both sides
+    for a, b, name in zip(g1, g0, "h_enc h_dec w1 b1 w2 b2".split()):
+        assert rel_err(a, b) < 6e-2, name   # gradient softmax evaluated on bf16-rounded logits in the fused path
