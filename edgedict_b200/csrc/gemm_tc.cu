@@ -31,11 +31,12 @@ constexpr int EPI_WARP_BYTES = 32 * 36 * 4;
 // EPW_ = epilogue warps: 4 (one per TMEM lane quadrant) or 8 (two per quadrant, alternating 32-column
 // chunks).  The epilogue of a short-K GEMM is latency-bound with a single warp per scheduler; with 8 warps
 // two of them interleave on every scheduler.  The wide tile then keeps 3 instead of 4 smem stages.
-template <int BN_, int EPW_ = 4> struct Cfg {
-    static constexpr int BN = BN_;
-    static constexpr int EPW = EPW_;
+// LOW_ = "co-resident" configuration: 3 stages of the narrow tile (115 KB of shared memory), so that a GEMM CTA
+// fits on an SM next to one CTA of a persistent recurrent kernel (lstm_tc.cu) -- used by the layer-wavefront
+// schedule of the encoder stack, where the input GEMM of one layer runs under the recurrence of another.
+template <int BN_, int EPW_ = 4, bool LOW_ = false> struct Cfg {
     static constexpr int NTHREADS = 64 + 32 * EPW_;
-    static constexpr int STAGES = BN_ == 256 ? (EPW_ == 8 ? 3 : 4) : 5;
+    static constexpr int STAGES = LOW_ ? 3 : (BN_ == 256 ? (EPW_ == 8 ? 3 : 4) : 5);
     static constexpr int B_BYTES = BN_ * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int TMEM_COLS = 2 * BN_;
@@ -147,12 +148,12 @@ struct LseArgs {
 // A_MN / B_MN: operand stored with its M (resp. N) index contiguous ("MN-major"), else K contiguous.
 //   K-major tile in smem : [128 rows][64 k] bf16, 128 B per row, 128B swizzle; SBO = 1024 (8 rows)
 //   MN-major tile in smem: 2 x [64 k][64 mn] bf16, 128 B per k-row; SBO = 1024 (8 k-rows), LBO = 8192
-template <bool A_MN, bool B_MN, int BN_, bool LSE = false, int EPW_ = 4>
+template <bool A_MN, bool B_MN, int BN_, bool LSE = false, int EPW_ = 4, bool LOW_ = false>
 __global__ void __launch_bounds__(64 + 32 * EPW_, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                void* __restrict__ Cout, int c_bf16, const float* __restrict__ bias, int accumulate,
                long M, int N, long K, int ksplit, LseArgs lse = LseArgs()) {
-    using C_ = Cfg<BN_, EPW_>;
+    using C_ = Cfg<BN_, EPW_, LOW_>;
     constexpr int BN = BN_, STAGES = C_::STAGES, STAGE_BYTES = C_::STAGE_BYTES;
     constexpr int TMEM_COLS = C_::TMEM_COLS, EPI_BYTES = C_::EPI_BYTES;
     extern __shared__ uint8_t smem_raw[];
@@ -488,6 +489,23 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, void* C, int c_bf16, co
     return EB_OK;
 }
 
+// co-resident configuration (see Cfg): plain nt GEMM, narrow tile, no split-K
+int launch_low(const CUtensorMap& ta, const CUtensorMap& tb, void* C, int c_bf16, const float* bias, int accumulate,
+               long M, int N, long K, cudaStream_t st) {
+    using C_ = Cfg<128, 4, true>;
+    auto kern = gemm_tc_kernel<false, false, 128, false, 4, true>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        EB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM_BYTES));
+        attr_done = true;
+    }
+    const long tiles = ((M + BM - 1) / BM) * ((N + 127) / 128);
+    const int grid = (int)(tiles < eb_num_sms() ? tiles : eb_num_sms());
+    kern<<<grid, C_::NTHREADS, C_::SMEM_BYTES, st>>>(ta, tb, C, c_bf16, bias, accumulate, M, N, K, 1, LseArgs());
+    EB_CHECK_LAUNCH();
+    return EB_OK;
+}
+
 template <int BN_>
 int launch_lse(const CUtensorMap& ta, const CUtensorMap& tb, void* C, const float* bias, long M, int N, long K,
                const LseArgs& lse, cudaStream_t st) {
@@ -536,7 +554,14 @@ EB_API int eb_joint_logits_lse(const void* hidden16, const void* w2_16, const fl
 
 EB_API int eb_gemm_bf16(const void* A, int a_mn_major, const void* B, int b_mn_major, void* C, int c_bf16,
                         const float* bias, int accumulate, long M, int N, long K, void* stream) {
+    return eb_gemm_bf16_ex(A, a_mn_major, B, b_mn_major, C, c_bf16, bias, accumulate, M, N, K, 0, stream);
+}
+
+EB_API int eb_gemm_bf16_ex(const void* A, int a_mn_major, const void* B, int b_mn_major, void* C, int c_bf16,
+                           const float* bias, int accumulate, long M, int N, long K, int flags, void* stream) {
     if (!A || !B || !C || M <= 0 || N <= 0 || K <= 0) return EB_ERR_INVALID;
+    const bool low = (flags & EB_GEMM_CORESIDENT) != 0;
+    if (low && (a_mn_major || b_mn_major)) return EB_ERR_INVALID;
     if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return EB_ERR_INVALID;
     // contiguous dimension must keep row pitches 16-byte aligned
     if ((a_mn_major ? M : K) % 8 || (b_mn_major ? (long)N : K) % 8) return EB_ERR_INVALID;
@@ -547,6 +572,7 @@ EB_API int eb_gemm_bf16(const void* A, int a_mn_major, const void* B, int b_mn_m
     bool wide = (N % 256 == 0) && (wide_tiles >= eb_num_sms() || (!c_bf16 && (K + BK - 1) / BK >= 64 && wide_tiles * 4 >= eb_num_sms()));
     if (force_bn == 128) wide = false;
     if (force_bn == 256 && N % 256 == 0) wide = true;
+    if (low) wide = false;
     CUtensorMap ta, tb;
     bool ok = a_mn_major ? make_map(&ta, A, (uint64_t)M, (uint64_t)K, 64) : make_map(&ta, A, (uint64_t)K, (uint64_t)M, 128);
     ok = ok && (b_mn_major ? make_map(&tb, B, (uint64_t)N, (uint64_t)K, 64)
@@ -556,6 +582,7 @@ EB_API int eb_gemm_bf16(const void* A, int a_mn_major, const void* B, int b_mn_m
         return EB_ERR_CUDA;
     }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (low) return launch_low(ta, tb, C, c_bf16, bias, accumulate, M, N, K, st);
 #define EB_GO(AM, BMN)                                                                              \
     return wide ? launch<AM, BMN, 256>(ta, tb, C, c_bf16, bias, accumulate, M, N, K, st)           \
                 : launch<AM, BMN, 128>(ta, tb, C, c_bf16, bias, accumulate, M, N, K, st)

@@ -31,6 +31,9 @@ namespace cg = cooperative_groups;
 
 namespace {
 
+#ifndef EB_LSTM_MINB
+#define EB_LSTM_MINB 2           // CTAs per SM the FORWARD kernel is compiled for (<= 128 registers / thread): the
+#endif                           // kernels of two LAYERS are co-resident on every SM in the wavefront schedule
 constexpr int NW = 8;            // warps per CTA
 constexpr int UPC = 8;           // hidden units finalised per CTA
 constexpr int PAD = 8;           // bf16 elements of row padding (16 B) -> conflict-free ldmatrix
@@ -40,6 +43,10 @@ constexpr size_t TC_HDR = 2048;  // scratch: [0,1024) grid barrier counter, [102
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(s), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
@@ -121,7 +128,7 @@ struct FwdP {
 // every SM and hide each other's barrier / exchange latency (the per-step critical path is latency,
 // not throughput: ~1 of 4 issue slots is used).
 template <int NBT>
-__global__ void __launch_bounds__(NW * 32, (NBT == 16) ? 2 : 1) lstm_tc_fwd_kernel(FwdP p) {
+__global__ void __launch_bounds__(NW * 32, (NBT == 16) ? 2 : EB_LSTM_MINB) lstm_tc_fwd_kernel(FwdP p) {
     constexpr int NT = NBT / 8;                              // batch n-tiles
     constexpr int SL = NT * 8;                               // accumulator slots per thread
     const int hb = blockIdx.y;                               // which batch tile
@@ -143,6 +150,10 @@ __global__ void __launch_bounds__(NW * 32, (NBT == 16) ? 2 : 1) lstm_tc_fwd_kern
     __nv_bfloat16* hs = reinterpret_cast<__nv_bfloat16*>(smraw);                 // [NBT][HP]
     float* red = reinterpret_cast<float*>(smraw + (size_t)NBT * HP * 2);         // [NW][SL][32]
     __nv_bfloat16* sh_h = reinterpret_cast<__nv_bfloat16*>(red + NW * SL * 32);   // [NBT][UPC]
+    // next step's input pre-activations are prefetched with cp.async into a per-thread shared slot: no
+    // registers are held across the grid barrier (a register prefetch is spilled at the 128-register
+    // budget of the two-CTAs-per-SM build, and the spill store waits for the DRAM round trip)
+    float* pxs = reinterpret_cast<float*>(sh_h + NBT * UPC) + threadIdx.x;         // [4][NW*32]
     const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
     const int j0 = blockIdx.x * UPC;
     const unsigned ncta = gridDim.x;
@@ -180,15 +191,14 @@ __global__ void __launch_bounds__(NW * 32, (NBT == 16) ? 2 : 1) lstm_tc_fwd_kern
     if (tid == 0) { __threadfence(); atomicAdd(p.bar, 1u); }
     unsigned epoch = 1;
 
-    // running pointers of this thread's (batch row, unit) element: advance by one frame per step
-    const float* xg_p = p.xg + (long)bb * T * 4 * H + j;
-    float* y_p = p.y + (long)bb * T * H + j;
-    __nv_bfloat16* y16_p = p.y16 ? p.y16 + (long)bb * T * H + j : nullptr;
-    float* g_p = p.gates ? p.gates + (long)bb * T * 4 * H + j : nullptr;
-    float* c_p = p.cseq ? p.cseq + (long)bb * T * H + j : nullptr;
-    float px[4];
+    // element offsets of this thread's (batch row, unit) pair in the [B,T,H] and [B,T,4H] tensors: advance by
+    // one frame per step (two offsets instead of five pointers: the kernel lives at 128 registers)
+    long oh = (long)bb * T * H + j;
+    long og4 = (long)bb * T * 4 * H + j;
+    if (own) {
 #pragma unroll
-    for (int g = 0; g < 4; ++g) px[g] = own ? __ldg(xg_p + (long)g * H) : 0.f;
+        for (int g = 0; g < 4; ++g) cp_async4(pxs + g * (NW * 32), p.xg + og4 + (long)g * H);
+    }
 
     for (int t = 0; t < T; ++t) {
         const __nv_bfloat16* hprev = p.hx + ((t + 1) & 1) * xstride;
@@ -247,6 +257,10 @@ __global__ void __launch_bounds__(NW * 32, (NBT == 16) ? 2 : 1) lstm_tc_fwd_kern
                 s[2] += r[(4 + off) * 32];
                 s[3] += r[(6 + off) * 32];
             }
+            cp_async_wait_all();                             // (already drained by warp_pull)
+            float px[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) px[g] = own ? pxs[g * (NW * 32)] : 0.f;
             ig = fast_sigmoid(s[0] + px[0]);
             fg = fast_sigmoid(s[1] + px[1]);
             gg = fast_tanh(s[2] + px[2]);
@@ -269,19 +283,16 @@ __global__ void __launch_bounds__(NW * 32, (NBT == 16) ? 2 : 1) lstm_tc_fwd_kern
         ++epoch;
         // everything below overlaps the other CTAs' progress towards the barrier
         if (own && !(p.dbg & 4)) {
-            *y_p = hn;
-            if (y16_p) *y16_p = __float2bfloat16(hn);
-            if (g_p) { g_p[0] = ig; g_p[H] = fg; g_p[2 * (long)H] = gg; g_p[3 * (long)H] = og; }
-            if (c_p) *c_p = c_state;
+            p.y[oh] = hn;
+            if (p.y16) p.y16[oh] = __float2bfloat16(hn);
+            if (p.gates) { float* g_p = p.gates + og4; g_p[0] = ig; g_p[H] = fg; g_p[2 * (long)H] = gg; g_p[3 * (long)H] = og; }
+            if (p.cseq) p.cseq[oh] = c_state;
             if (t == T - 1) { p.hT[(long)bb * H + j] = hn; p.cT[(long)bb * H + j] = c_state; }
         }
-        y_p += H; xg_p += 4 * (long)H;
-        if (y16_p) y16_p += H;
-        if (g_p) g_p += 4 * (long)H;
-        if (c_p) c_p += H;
-        if (t + 1 < T) {
+        oh += H; og4 += 4 * (long)H;
+        if (t + 1 < T && own) {
 #pragma unroll
-            for (int g = 0; g < 4; ++g) px[g] = own ? __ldg(xg_p + (long)g * H) : 0.f;
+            for (int g = 0; g < 4; ++g) cp_async4(pxs + g * (NW * 32), p.xg + og4 + (long)g * H);
         }
     }
 }
@@ -315,6 +326,7 @@ __global__ void __launch_bounds__(NW * 32, 1) lstm_tc_bwd_kernel(BwdP p) {
     float* part = red + NW * SLOTS * 32;                                         // [2][JS][NB] (step parity)
     __nv_bfloat16* sg = reinterpret_cast<__nv_bfloat16*>(part + 2 * JS * NB);    // [NB][4][UPC]  (gate-major, for dg16)
     __nv_bfloat16* sx = sg + NB * 4 * UPC;                                       // [NB][UPC][4]  (unit-major, exchange)
+    float* pgs = reinterpret_cast<float*>(sx + NB * UPC * 4) + threadIdx.x;      // [4][NW*32] cp.async prefetch slots (gates)
     const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
     const int rs = blockIdx.x % CS;                          // K slice (= cluster rank)
     const int js = blockIdx.x / CS;                          // unit group
@@ -358,12 +370,13 @@ __global__ void __launch_bounds__(NW * 32, 1) lstm_tc_bwd_kernel(BwdP p) {
     unsigned epoch = 0;
 
     // prefetched inputs of the gate-gradient math: gates i,f,g,o, c_t, c_{t-1}, dy_t
-    float in0 = 0.f, in1 = 0.f, in2 = 0.f, in3 = 0.f, in4 = 0.f, in5 = 0.f, in6 = 0.f;
+    // (the four gates go through cp.async + shared memory, see the forward kernel; c_t, c_{t-1}, dy_t in registers)
+    float in4 = 0.f, in5 = 0.f, in6 = 0.f;
 #define EB_PREFETCH(tt)                                                                                   \
     if (own && (tt) >= 0) {                                                                               \
         const long bt_ = (long)bb * T + (tt);                                                             \
         const float* gp_ = p.gates + bt_ * H4 + j;                                                        \
-        in0 = __ldg(gp_); in1 = __ldg(gp_ + H); in2 = __ldg(gp_ + 2 * (long)H); in3 = __ldg(gp_ + 3 * (long)H); \
+        _Pragma("unroll") for (int g_ = 0; g_ < 4; ++g_) cp_async4(pgs + g_ * (NW * 32), gp_ + (long)g_ * H); \
         in4 = __ldg(p.cseq + bt_ * H + j);                                                                \
         in5 = ((tt) > 0) ? __ldg(p.cseq + (bt_ - 1) * H + j) : (p.c0 ? p.c0[(long)bb * H + j] : 0.f);     \
         in6 = __ldg(p.dy + bt_ * H + j);                                                                  \
@@ -376,7 +389,8 @@ __global__ void __launch_bounds__(NW * 32, 1) lstm_tc_bwd_kernel(BwdP p) {
         {
             float da[4] = {0.f, 0.f, 0.f, 0.f};
             if (own) {
-                const float ig = in0, fg = in1, gg = in2, og = in3;
+                cp_async_wait_all();                         // (already drained by warp_pull, except at t = T-1)
+                const float ig = pgs[0], fg = pgs[NW * 32], gg = pgs[2 * NW * 32], og = pgs[3 * NW * 32];
                 const float tc = fast_tanh(in4);
                 const float dht = in6 + dh;
                 const float dct = dc + dht * og * (1.f - tc * tc);
@@ -493,7 +507,10 @@ inline bool tc_ok(int B, int H) { return H % 64 == 0 && H <= 1024 && B >= 1; }
 
 template <int CS>
 size_t bwd_smem(int H) {
-    return (size_t)NB * (4 * H / CS + PAD) * 2 + sizeof(float) * (NW * (CS / 2) * 16 * 32 + 2 * 8 * CS * NB) + 2 * NB * 4 * UPC * 2;
+    static int pad = -1;
+    if (pad < 0) { const char* e = getenv("EDGEDICT_LSTM_PADSMEM_BWD"); pad = e ? atoi(e) * 1024 : 0; }   // placement experiments
+    return (size_t)pad + (size_t)NB * (4 * H / CS + PAD) * 2 + sizeof(float) * (NW * (CS / 2) * 16 * 32 + 2 * 8 * CS * NB) + 2 * NB * 4 * UPC * 2 +
+           sizeof(float) * 4 * NW * 32;
 }
 
 template <int CS>
@@ -596,7 +613,7 @@ EB_API int eb_lstm_tc_fwd(const float* xg, const void* whh16, const float* h0, c
         split = e ? (atoi(e) ? 1 : 0) : 0;     // measured: no gain (each half is as latency-bound as the whole), off by default
         if (split) {
             int nblk = 0;
-            const size_t sm16 = (size_t)16 * (1024 + PAD) * 2 + sizeof(float) * NW * 16 * 32 + 16 * UPC * 2;
+            const size_t sm16 = (size_t)16 * (1024 + PAD) * 2 + sizeof(float) * NW * 16 * 32 + 16 * UPC * 2 + sizeof(float) * 4 * NW * 32;
             cudaFuncSetAttribute(lstm_tc_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm16);
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, lstm_tc_fwd_kernel<16>, NW * 32, sm16) != cudaSuccess || nblk < 2) {
                 (void)cudaGetLastError();
@@ -605,7 +622,8 @@ EB_API int eb_lstm_tc_fwd(const float* xg, const void* whh16, const float* h0, c
         }
     }
     const int nbt = split ? 16 : 32;
-    const size_t smem = (size_t)nbt * (H + PAD) * 2 + sizeof(float) * NW * (nbt / 8) * 8 * 32 + nbt * UPC * 2;
+    size_t smem = (size_t)nbt * (H + PAD) * 2 + sizeof(float) * NW * (nbt / 8) * 8 * 32 + nbt * UPC * 2 + sizeof(float) * 4 * NW * 32;
+    { const char* e = getenv("EDGEDICT_LSTM_PADSMEM"); if (e) smem += (size_t)atoi(e) * 1024; }   // placement experiments
     if (split) EB_CUDA(cudaFuncSetAttribute(lstm_tc_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     else EB_CUDA(cudaFuncSetAttribute(lstm_tc_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int b0 = 0; b0 < B; b0 += NB) {

@@ -162,6 +162,215 @@ class LSTMLayer(torch.autograd.Function):
                 dw_ih, dw_hh, db, db.clone(), None)
 
 
+# ---- layer-wavefront schedule of the LSTM stack ------------------------------------------------------------
+# The recurrence of one layer is a chain of T grid-synchronous steps that is bound by exchange/barrier LATENCY
+# (DESIGN.md section 7): one layer's persistent kernel uses ~1 of 4 issue slots of 128 SMs.  Layer l+1 at frame t
+# only needs layer l up to frame t, so the time axis is cut into chunks and layer l+1 runs chunk c on a second
+# stream while layer l runs chunk c+1: two persistent kernels (compiled for <= 128 registers, ~100 KB of shared
+# memory each) are co-resident on every SM and hide each other's latency.  The per-chunk input GEMM uses the
+# co-resident tile configuration (EB_GEMM_CORESIDENT) so that it fits next to the other layer's recurrent CTA.
+WAVEFRONT_CHUNKS = int(os.environ.get("EDGEDICT_WAVEFRONT_CHUNKS", "4"))     # 0 disables; 4/6/8 measured: 66.5/67.3/67.8 ms
+_wave_streams = {}
+
+
+def _side_streams(device):
+    st = _wave_streams.get(device)
+    if st is None:
+        st = _wave_streams[device] = (torch.cuda.Stream(device), torch.cuda.Stream(device))
+    return st
+
+
+def wavefront_plan(T, reductions, max_chunks=None):
+    """Chunk lengths per layer for the wavefront schedule, or None when T is too short to cut.
+    Chunk boundaries are multiples of 2^(number of time reductions) so that TimeReduction pairs never straddle
+    a boundary; only the last chunk may be ragged (its zero padding is the reference's padding of the last
+    frame, rnnt/models.py:24-27).  Returns a list (len L+1) of per-chunk lengths on each layer's time axis."""
+    max_chunks = WAVEFRONT_CHUNKS if max_chunks is None else max_chunks
+    if max_chunks < 2:
+        return None
+    gran = 1 << sum(1 for r in reductions if r)
+    step = -(-T // (max_chunks * gran)) * gran
+    if step < 16 * gran:                     # too short to amortise the per-chunk launches
+        step = 16 * gran
+    lens = [min(step, T - t0) for t0 in range(0, T, step)]
+    if len(lens) < 2:
+        return None
+    plan = [lens]
+    for r in reductions:
+        lens = [(n + 1) // 2 for n in lens] if r else lens
+        plan.append(lens)
+    return plan
+
+
+class _Chunks:
+    """Chunk-major storage: the [B, Tc, D] blocks of all chunks back to back in one [B*T, D] buffer.  Row-wise
+    kernels (LayerNorm, casts, the bulk GEMMs of the backward pass) run on the flat buffer, time-ordered ones
+    (the recurrence, TimeReduction) on one block."""
+
+    def __init__(self, B, lens):
+        self.B, self.lens = B, lens
+        self.off = [0]
+        for n in lens:
+            self.off.append(self.off[-1] + n)
+        self.rows = B * self.off[-1]
+
+    def new(self, D, dtype, device):
+        return torch.empty(self.rows, D, dtype=dtype, device=device) if D else torch.empty(self.rows, dtype=dtype, device=device)
+
+    def blk(self, buf, c):
+        a, b = self.B * self.off[c], self.B * self.off[c + 1]
+        v = buf[a:b]
+        return v.view(self.B, self.lens[c], buf.shape[1]) if buf.dim() == 2 else v
+
+    def scatter(self, x):
+        """[B, T, D] -> chunk-major flat buffer."""
+        out = self.new(x.shape[2], x.dtype, x.device)
+        for c in range(len(self.lens)):
+            self.blk(out, c).copy_(x[:, self.off[c]:self.off[c + 1]])
+        return out
+
+    def gather(self, buf):
+        """chunk-major flat buffer -> [B, T, D]."""
+        out = torch.empty(self.B, self.off[-1], buf.shape[1], dtype=buf.dtype, device=buf.device)
+        for c in range(len(self.lens)):
+            out[:, self.off[c]:self.off[c + 1]].copy_(self.blk(buf, c))
+        return out
+
+
+class LSTMStack(torch.autograd.Function):
+    """ResLayerNormLSTM.forward (rnnt/models.py:57-75) for all layers at once, bf16 tensor-core mode, zero
+    initial state: per layer nn.LSTM -> LayerNorm(y + x) (no residual for layer 0) -> optional TimeReduction,
+    executed as a layer wavefront over time chunks on two streams (see above).  Numerically identical to the
+    layer-by-layer Functions (same kernels, same per-row / per-step arithmetic); the backward pass reuses their
+    kernels on the chunk-major buffers, the BPTT kernel once per chunk with the (dh, dc) carry.
+    args: x [B,T,I] fp32, cfg = (reductions, eps, plan), then per layer w_ih, w_hh, b_ih, b_hh, ln_w, ln_b.
+    returns y [B,T',H], h_T [L,B,H], c_T [L,B,H] (final states: not differentiated through)."""
+
+    @staticmethod
+    def forward(ctx, x, cfg, *params):
+        reductions, eps, plan = cfg
+        L = len(reductions)
+        B, T, I0 = x.shape
+        dev = x.device
+        H = params[1].shape[1]
+        C = len(plan[0])
+        need = any(ctx.needs_input_grad)
+        ck = [_Chunks(B, lens) for lens in plan]
+        P = [params[6 * l:6 * l + 6] for l in range(L)]
+        wih16 = [ops.cast_bf16(_c(p[0])) for p in P]
+        whh16 = [ops.cast_bf16(_c(p[1])) for p in P]
+        bias = [p[2] + p[3] for p in P]
+        x16 = [ck[0].scatter(ops.cast_bf16(_c(x)))] + [None] * L
+        xs = [None] * (L + 1)                                # fp32 layer inputs (LayerNorm residuals), l >= 1
+        y, y16, gates, cseq, mean, rstd = ([None] * L for _ in range(6))
+        z = [None] * L
+        for l in range(L):
+            k, kn = ck[l], ck[l + 1]
+            y[l] = k.new(H, f32, dev)
+            y16[l] = k.new(H, bf16, dev)
+            gates[l] = k.new(4 * H, f32, dev) if need else None
+            cseq[l] = k.new(H, f32, dev) if need else None
+            mean[l], rstd[l] = k.new(0, f32, dev), k.new(0, f32, dev)
+            xs[l + 1] = kn.new(H, f32, dev)
+            z[l] = k.new(H, f32, dev) if reductions[l] else xs[l + 1]
+            x16[l + 1] = kn.new(H, bf16, dev) if l + 1 < L else None
+        hT = torch.empty(L, C, B, H, dtype=f32, device=dev)
+        cT = torch.empty(L, C, B, H, dtype=f32, device=dev)
+        xgbuf = [torch.empty(B * max(plan[0]), 4 * H, dtype=f32, device=dev) for _ in range(2)]
+
+        main = torch.cuda.current_stream(dev)
+        side = _side_streams(dev)
+        done = [[torch.cuda.Event() for _ in range(C)] for _ in range(L)]
+        for s in side:
+            s.wait_stream(main)
+        for d in range(L + C - 1):
+            for l in range(max(0, d - C + 1), min(L, d + 1)):
+                c = d - l
+                k, kn = ck[l], ck[l + 1]
+                s = side[l % 2]
+                with torch.cuda.stream(s):
+                    if l > 0:
+                        s.wait_event(done[l - 1][c])
+                    Tc = k.lens[c]
+                    xin = k.blk(x16[l], c)
+                    xg = xgbuf[l % 2][:B * Tc]
+                    ops.gemm_bf16(xin.view(B * Tc, xin.shape[2]), 0, wih16[l], 0, B * Tc, 4 * H, xin.shape[2],
+                                  bias=bias[l], out=xg, flags=ops.GEMM_CORESIDENT)
+                    ops.lstm_tc_fwd(xg.view(B, Tc, 4 * H), whh16[l], hT[l, c - 1] if c else None,
+                                    cT[l, c - 1] if c else None, need,
+                                    out=(k.blk(y[l], c), k.blk(y16[l], c), hT[l, c], cT[l, c],
+                                         k.blk(gates[l], c) if need else None, k.blk(cseq[l], c) if need else None))
+                    res = k.blk(xs[l], c) if l else None
+                    nx16 = kn.blk(x16[l + 1], c) if x16[l + 1] is not None else None
+                    if reductions[l]:
+                        ops.layernorm_fwd(k.blk(y[l], c), res, P[l][4], P[l][5], eps[l],
+                                          out=(k.blk(z[l], c), None, k.blk(mean[l], c), k.blk(rstd[l], c)))
+                        ops.time_reduce_fwd(k.blk(z[l], c), out=(kn.blk(xs[l + 1], c), nx16))
+                    else:
+                        ops.layernorm_fwd(k.blk(y[l], c), res, P[l][4], P[l][5], eps[l],
+                                          out=(kn.blk(xs[l + 1], c), nx16, k.blk(mean[l], c), k.blk(rstd[l], c)))
+                    done[l][c].record(s)
+        for s in side:
+            main.wait_stream(s)
+        out = ck[L].gather(xs[L])
+        hT_last, cT_last = hT[:, C - 1].contiguous(), cT[:, C - 1].contiguous()
+        if need:
+            ctx.save_for_backward(*params, hT, cT, *x16[:L], *xs[1:L], *y, *y16, *gates, *cseq, *mean, *rstd)
+            ctx.cfg, ctx.dims = cfg, (B, T, I0, H, L, C)
+        ctx.mark_non_differentiable(hT_last, cT_last)
+        return out, hT_last, cT_last
+
+    @staticmethod
+    def backward(ctx, dout, _dh, _dc):
+        reductions, eps, plan = ctx.cfg
+        B, T, I0, H, L, C = ctx.dims
+        sv = list(ctx.saved_tensors)
+        params, sv = sv[:6 * L], sv[6 * L:]
+        hT, cT = sv[0], sv[1]
+        sv = sv[2:]
+        x16, sv = sv[:L], sv[L:]
+        xs, sv = [None] + sv[:L - 1], sv[L - 1:]
+        y, y16, gates, cseq, mean, rstd = (sv[i * L:(i + 1) * L] for i in range(6))
+        P = [params[6 * l:6 * l + 6] for l in range(L)]
+        ck = [_Chunks(B, lens) for lens in plan]
+        dev = dout.device
+        g = ck[L].scatter(_c(dout))                           # d xs[L], chunk-major
+        grads = [None] * (6 * L)
+        for l in range(L - 1, -1, -1):
+            k, kn = ck[l], ck[l + 1]
+            if reductions[l]:
+                gz = k.new(H, f32, dev)
+                for c in range(C):
+                    ops.time_reduce_bwd(kn.blk(g, c), k.lens[c], out=k.blk(gz, c))
+                g = gz
+            dz, dgamma, dbeta = ops.layernorm_bwd(g, y[l], xs[l], P[l][4], mean[l], rstd[l])
+            whhT16 = ops.transpose_to_bf16(_c(P[l][1]))
+            dg16 = k.new(4 * H, bf16, dev)
+            hprev = k.new(H, bf16, dev)
+            dh = dc = None
+            for c in range(C - 1, -1, -1):
+                _, dh, dc = ops.lstm_tc_bwd(k.blk(dz, c), k.blk(gates[l], c), k.blk(cseq[l], c),
+                                            cT[l, c - 1] if c else None, whhT16, dh, dc, out=k.blk(dg16, c))
+                hp, yc = k.blk(hprev, c), k.blk(y16[l], c)
+                hp[:, 1:] = yc[:, :-1]
+                if c:
+                    hp[:, 0] = k.blk(y16[l], c - 1)[:, -1]
+                else:
+                    hp[:, 0].zero_()
+            dx = ops.mm_nn(dg16, P[l][0], "bf16", dy16=dg16) if (l > 0 or ctx.needs_input_grad[0]) else None
+            grads[6 * l + 0] = ops.mm_tn(dg16, x16[l], "bf16", dy16=dg16, x16=x16[l])
+            grads[6 * l + 1] = ops.mm_tn(dg16, hprev, "bf16", dy16=dg16, x16=hprev)
+            db = ops.colsum(dg16)
+            grads[6 * l + 2], grads[6 * l + 3] = db, db.clone()
+            grads[6 * l + 4], grads[6 * l + 5] = dgamma, dbeta
+            if l > 0:
+                g = dx.add_(dz)                               # through the LSTM input + the LayerNorm residual
+            else:
+                g = dx
+        dxin = ck[0].gather(g) if g is not None else None
+        return (dxin, None, *grads)
+
+
 def _joint_pre(h_enc, h_dec, w1, b1, precision):
     """ep = W1[:, :E] h_enc + b1, dp = W1[:, E:] h_dec  -- exact split of Linear(cat[e, d])."""
     B, T, E = h_enc.shape

@@ -82,9 +82,9 @@ class _timed:
         return False
 
 
-def cast_bf16(x):
+def cast_bf16(x, out=None):
     _need(x, f32, "x")
-    y = torch.empty(x.shape, dtype=bf16, device=x.device)
+    y = out if out is not None else torch.empty(x.shape, dtype=bf16, device=x.device)
     n = x.numel()
     if n:
         check(lib().eb_cast_bf16(_p(x), _p(y), n, _s()), "eb_cast_bf16")
@@ -101,13 +101,16 @@ def gemm_f32(A, sam, sak, B, sbk, sbn, M, N, K, bias=None, out=None, beta=0.0, a
     return out
 
 
-def gemm_bf16(A, a_mn, B, b_mn, M, N, K, bias=None, out=None, out_bf16=False, accumulate=False, tag=None):
+GEMM_CORESIDENT = 1      # include/edgedict_b200.h EB_GEMM_CORESIDENT
+
+
+def gemm_bf16(A, a_mn, B, b_mn, M, N, K, bias=None, out=None, out_bf16=False, accumulate=False, tag=None, flags=0):
     if out is None:
         out = torch.empty(M, N, dtype=bf16 if out_bf16 else f32, device=A.device)
     name = tag or ("gemm_bf16_%s%s" % ("t" if a_mn else "n", "n" if b_mn else "t"))
     with _timed(name, 1, 2.0 * (M * K + N * K) + out.element_size() * M * N, 2.0 * M * N * K):
-        check(lib().eb_gemm_bf16(_p(A), int(a_mn), _p(B), int(b_mn), _p(out), int(out.dtype == bf16), _p(bias),
-                                 int(accumulate), M, N, K, _s()), "eb_gemm_bf16")
+        check(lib().eb_gemm_bf16_ex(_p(A), int(a_mn), _p(B), int(b_mn), _p(out), int(out.dtype == bf16), _p(bias),
+                                    int(accumulate), M, N, K, int(flags), _s()), "eb_gemm_bf16")
     return out
 
 
@@ -158,13 +161,17 @@ def colsum(x, out=None):
 
 
 # ---- LayerNorm / TimeReduction / Embedding -------------------------------------------------------
-def layernorm_fwd(x, res, gamma, beta, eps=1e-5, want_bf16=False):
+def layernorm_fwd(x, res, gamma, beta, eps=1e-5, want_bf16=False, out=None):
+    """out = (y, y16 | None, mean, rstd) preallocated (contiguous slices of larger buffers), or None."""
     H = x.shape[-1]
     rows = x.numel() // H
-    y = torch.empty_like(x)
-    y16 = torch.empty(x.shape, dtype=bf16, device=x.device) if want_bf16 else None
-    mean = torch.empty(rows, dtype=f32, device=x.device)
-    rstd = torch.empty(rows, dtype=f32, device=x.device)
+    if out is not None:
+        y, y16, mean, rstd = out
+    else:
+        y = torch.empty_like(x)
+        y16 = torch.empty(x.shape, dtype=bf16, device=x.device) if want_bf16 else None
+        mean = torch.empty(rows, dtype=f32, device=x.device)
+        rstd = torch.empty(rows, dtype=f32, device=x.device)
     check(lib().eb_layernorm_fwd(_p(x), _p(res), _p(gamma), _p(beta), _p(y), _p(y16), _p(mean), _p(rstd),
                                  rows, H, eps, _s()), "eb_layernorm_fwd")
     return y, y16, mean, rstd
@@ -181,17 +188,20 @@ def layernorm_bwd(dy, x, res, gamma, mean, rstd):
     return dz, dgamma, dbeta
 
 
-def time_reduce_fwd(x, want_bf16=False):
+def time_reduce_fwd(x, want_bf16=False, out=None):
     B, T, H = x.shape
-    y = torch.empty(B, (T + 1) // 2, H, dtype=f32, device=x.device)
-    y16 = torch.empty(y.shape, dtype=bf16, device=x.device) if want_bf16 else None
+    if out is not None:
+        y, y16 = out
+    else:
+        y = torch.empty(B, (T + 1) // 2, H, dtype=f32, device=x.device)
+        y16 = torch.empty(y.shape, dtype=bf16, device=x.device) if want_bf16 else None
     check(lib().eb_time_reduce_fwd(_p(x), _p(y), _p(y16), B, T, H, _s()), "eb_time_reduce_fwd")
     return y, y16
 
 
-def time_reduce_bwd(dy, T):
+def time_reduce_bwd(dy, T, out=None):
     B, _, H = dy.shape
-    dx = torch.empty(B, T, H, dtype=f32, device=dy.device)
+    dx = out if out is not None else torch.empty(B, T, H, dtype=f32, device=dy.device)
     check(lib().eb_time_reduce_bwd(_p(dy), _p(dx), B, T, H, _s()), "eb_time_reduce_bwd")
     return dx
 
@@ -264,7 +274,7 @@ def lstm_tc_supported(B, H):
 
 
 def _lstm_tc_scratch(B, H, device):
-    key = ("tc", H, device)
+    key = ("tc", H, device, _s())     # one exchange buffer + barrier block per stream: kernels of two layers overlap
     t = _scratch.get(key)
     if t is None:
         t = torch.zeros(lib().eb_lstm_tc_scratch_bytes(B, H), dtype=torch.uint8, device=device)
@@ -272,26 +282,30 @@ def _lstm_tc_scratch(B, H, device):
     return t
 
 
-def lstm_tc_fwd(xg, whh16, h0, c0, save):
+def lstm_tc_fwd(xg, whh16, h0, c0, save, out=None):
+    """out = (y, y16, hT, cT, gates | None, cseq | None) preallocated, or None."""
     B, T, H4 = xg.shape
     H = H4 // 4
     dev = xg.device
-    y = torch.empty(B, T, H, dtype=f32, device=dev)
-    y16 = torch.empty(B, T, H, dtype=bf16, device=dev)
-    hT = torch.empty(B, H, dtype=f32, device=dev)
-    cT = torch.empty(B, H, dtype=f32, device=dev)
-    gates = torch.empty(B, T, H4, dtype=f32, device=dev) if save else None
-    cseq = torch.empty(B, T, H, dtype=f32, device=dev) if save else None
+    if out is not None:
+        y, y16, hT, cT, gates, cseq = out
+    else:
+        y = torch.empty(B, T, H, dtype=f32, device=dev)
+        y16 = torch.empty(B, T, H, dtype=bf16, device=dev)
+        hT = torch.empty(B, H, dtype=f32, device=dev)
+        cT = torch.empty(B, H, dtype=f32, device=dev)
+        gates = torch.empty(B, T, H4, dtype=f32, device=dev) if save else None
+        cseq = torch.empty(B, T, H, dtype=f32, device=dev) if save else None
     with _timed("lstm_tc_fwd", 1, 0.0, 2.0 * B * T * 4 * H * H):
         check(lib().eb_lstm_tc_fwd(_p(xg), _p(whh16), _p(h0), _p(c0), _p(y), _p(y16), _p(hT), _p(cT), _p(gates),
                                    _p(cseq), _p(_lstm_tc_scratch(B, H, dev)), B, T, H, _s()), "eb_lstm_tc_fwd")
     return y, y16, hT, cT, gates, cseq
 
 
-def lstm_tc_bwd(dy, gates, cseq, c0, whhT16, dhT, dcT):
+def lstm_tc_bwd(dy, gates, cseq, c0, whhT16, dhT, dcT, out=None):
     B, T, H = dy.shape
     dev = dy.device
-    dg16 = torch.empty(B, T, 4 * H, dtype=bf16, device=dev)
+    dg16 = out if out is not None else torch.empty(B, T, 4 * H, dtype=bf16, device=dev)
     dh0 = torch.empty(B, H, dtype=f32, device=dev)
     dc0 = torch.empty(B, H, dtype=f32, device=dev)
     with _timed("lstm_tc_bwd", 1, 0.0, 2.0 * B * T * 4 * H * H):

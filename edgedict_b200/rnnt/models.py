@@ -70,8 +70,35 @@ class ResLayerNormLSTM(nn.Module):
             self.projs.append(nn.Sequential(*stack))
             input_size = hidden_size
 
+    def _wavefront_cfg(self, xs, p):
+        """(cfg, params) of the layer-wavefront schedule (functional.LSTMStack) when it applies: bf16 tensor-core
+        mode, zero initial state, no active dropout, a sequence long enough to be cut into chunks."""
+        if p != "bf16" or len(self.lstms) < 2 or not xs.is_cuda:
+            return None
+        B, T = xs.shape[0], xs.shape[1]
+        if not ops.lstm_tc_supported(B, self.hidden_size):
+            return None
+        reductions, eps, params = [], [], []
+        for cell, post in zip(self.lstms, self.projs):
+            extras = list(post)[1:]
+            if any(isinstance(m, nn.Dropout) and self.training and m.p > 0 for m in extras):
+                return None
+            reductions.append(any(isinstance(m, TimeReduction) for m in extras))
+            eps.append(post[0].eps)
+            params += [cell.weight_ih_l0, cell.weight_hh_l0, cell.bias_ih_l0, cell.bias_hh_l0,
+                       post[0].weight, post[0].bias]
+        plan = Fn.wavefront_plan(T, reductions)
+        if plan is None:
+            return None
+        return (tuple(reductions), tuple(eps), plan), params
+
     def forward(self, xs, hiddens=None):
         p = _precision(self)
+        if hiddens is None:
+            wf = self._wavefront_cfg(xs, p)
+            if wf is not None:
+                out, hT, cT = Fn.LSTMStack.apply(xs, wf[0], *wf[1])
+                return out, (hT, cT)
         hs, cs = (None, None) if hiddens is None else hiddens
         out_h, out_c = [], []
         for i, (cell, post) in enumerate(zip(self.lstms, self.projs)):

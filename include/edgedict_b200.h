@@ -56,6 +56,13 @@ int eb_gemm_f32(const float* A, long sam, long sak, const float* B, long sbk, lo
 int eb_gemm_bf16(const void* A, int a_mn_major, const void* B, int b_mn_major, void* C, int c_bf16,
                  const float* bias, int accumulate, long M, int N, long K, void* stream);
 
+/* eb_gemm_bf16 with launch flags.  EB_GEMM_CORESIDENT (A and B K-major only): a 115 KB / 192-thread
+ * configuration that shares an SM with one CTA of a persistent recurrent kernel (eb_lstm_tc_fwd), used by the
+ * layer-wavefront schedule of the encoder stack (functional.LSTMStack). */
+#define EB_GEMM_CORESIDENT 1
+int eb_gemm_bf16_ex(const void* A, int a_mn_major, const void* B, int b_mn_major, void* C, int c_bf16,
+                    const float* bias, int accumulate, long M, int N, long K, int flags, void* stream);
+
 /* joint output layer + softmax statistics in one GEMM (bf16 mode): replaces the second Linear of Joint
  * (rnnt/models.py:165) together with reduce_max/reduce_exp (warp-transducer reduce.h:45-104) and the
  * blank/label gathers of the lattice kernels.  denom/lpb/lpl: the first three arrays of the loss workspace. */

@@ -184,3 +184,34 @@ def test_fused_joint_lse_path_matches_unfused_bf16_path(B, T, U, E, D, J, V):
     assert rel_err(c1, c0) < 2e-3           # same bf16 operands; statistics from fp32 accumulators on both sides
     for a, b, name in zip(g1, g0, "h_enc h_dec w1 b1 w2 b2".split()):
         assert rel_err(a, b) < 6e-2, name   # gradient softmax evaluated on bf16-rounded logits in the fused path
+
+
+@pytest.mark.parametrize("B,T,L,red,H", [(3, 70, 3, (1,), 64), (2, 133, 4, (0, 2), 128), (33, 48, 2, (1,), 64)])
+def test_layer_wavefront_stack_matches_layer_by_layer(B, T, L, red, H):
+    """functional.LSTMStack (time-chunked layer wavefront on two streams, chunk-major buffers, chunked BPTT with
+    the (dh, dc) carry) against the layer-by-layer Functions: same kernels and arithmetic, so outputs, final
+    states and every gradient agree to fp32 round-off of the bulk GEMMs' different summation splits."""
+    from edgedict_b200 import functional as Fn
+    from edgedict_b200.rnnt.models import ResLayerNormLSTM
+    torch.manual_seed(T)
+    net = ResLayerNormLSTM(40, H, L, time_reductions=list(red)).cuda()
+    for m in net.modules():
+        m.precision = "bf16"
+    x = torch.randn(B, T, 40).cuda()
+    w = torch.randn(B, T, H).cuda()
+    res = []
+    for chunks in (0, 4):
+        Fn.WAVEFRONT_CHUNKS = chunks
+        net.zero_grad()
+        xi = x.clone().requires_grad_(True)
+        y, (hT, cT) = net(xi)
+        assert (Fn.wavefront_plan(T, [i in red for i in range(L)]) is not None) == (chunks > 0)
+        (y * w[:, :y.shape[1]]).sum().backward()
+        res.append((y.detach().cpu(), hT.detach().cpu(), cT.detach().cpu(), xi.grad.cpu(), [p.grad.cpu().clone() for p in net.parameters()]))
+    Fn.WAVEFRONT_CHUNKS = int(__import__("os").environ.get("EDGEDICT_WAVEFRONT_CHUNKS", "4"))
+    (y0, h0, c0, dx0, g0), (y1, h1, c1, dx1, g1) = res
+    assert y0.shape == y1.shape
+    assert rel_err(y1, y0) < 1e-5 and rel_err(h1, h0) < 1e-5 and rel_err(c1, c0) < 1e-5
+    assert rel_err(dx1, dx0) < 2e-3
+    for a, b, (name, _) in zip(g1, g0, net.named_parameters()):
+        assert rel_err(a, b) < 2e-3, name
