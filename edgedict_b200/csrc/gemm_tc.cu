@@ -452,14 +452,26 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, void* C, int c_bf16, co
     constexpr int BN = BN_;
     const long out_tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     const long nkb = (K + BK - 1) / BK;
-    // split-K (weight gradients: few output tiles, contraction over millions of rows): fill the
-    // machine ~2x over, keep >= 16 k-blocks per split; partial tiles are reduced with fp32 atomics
+    // split-K (weight gradients: few output tiles, contraction over up to millions of rows).  The persistent grid
+    // processes tiles*ksplit work items in waves of one per SM; a ragged last wave idles most of the machine
+    // (20 tiles x 15 splits = 300 items = 2.03 waves ran at 67 %), so ksplit is chosen to fill whole waves:
+    // maximise  wave efficiency / (1 + r * ksplit / nkb):  items / (waves * SMs) against the cost of one more
+    // atomic tile epilogue per split, which was measured at r ~ 32 k-blocks of MMA time for the 128x256 tile
+    // (lstm dW, 128 tiles, 500 k-blocks: ksplit 3 -> 228 us, 8 -> 254 us; joint dW2, 20 tiles, 32250 k-blocks:
+    // ksplit 15 -> 3.7 ms, 22 -> 2.8 ms).  Partial tiles are reduced with fp32 atomics.
     int ksplit = 1;
-    if (!c_bf16 && out_tiles < eb_num_sms() && nkb >= 64) {
-        long want = (2L * eb_num_sms() + out_tiles - 1) / out_tiles;
+    if (!c_bf16 && nkb >= 64 && out_tiles < eb_num_sms()) {
+        const long S = eb_num_sms();
         long cap = nkb / 16;
-        ksplit = (int)(want < cap ? want : cap);
-        if (ksplit < 1) ksplit = 1;
+        if (cap > 64) cap = 64;
+        const double r = BN == 256 ? 32.0 : 16.0;
+        double best = -1.0;
+        for (long ks = 1; ks <= cap; ++ks) {
+            const long items = out_tiles * ks;
+            const long waves = (items + S - 1) / S;
+            const double score = (double)items / (double)(waves * S) / (1.0 + r * (double)ks / (double)nkb);
+            if (score > best) { best = score; ksplit = (int)ks; }
+        }
     }
     if (ksplit > 1 && !accumulate) EB_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, st));
     const long tiles = out_tiles * ksplit;

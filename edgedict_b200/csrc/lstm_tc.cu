@@ -325,8 +325,7 @@ __global__ void __launch_bounds__(NW * 32, 1) lstm_tc_bwd_kernel(BwdP p) {
     float* red = reinterpret_cast<float*>(smraw + (size_t)NB * KP * 2);          // [NW][SLOTS][32]
     float* part = red + NW * SLOTS * 32;                                         // [2][JS][NB] (step parity)
     __nv_bfloat16* sg = reinterpret_cast<__nv_bfloat16*>(part + 2 * JS * NB);    // [NB][4][UPC]  (gate-major, for dg16)
-    __nv_bfloat16* sx = sg + NB * 4 * UPC;                                       // [NB][UPC][4]  (unit-major, exchange)
-    float* pgs = reinterpret_cast<float*>(sx + NB * UPC * 4) + threadIdx.x;      // [4][NW*32] cp.async prefetch slots (gates)
+    float* pgs = reinterpret_cast<float*>(sg + NB * 4 * UPC) + threadIdx.x;      // [4][NW*32] cp.async prefetch slots (gates)
     const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
     const int rs = blockIdx.x % CS;                          // K slice (= cluster rank)
     const int js = blockIdx.x / CS;                          // unit group
@@ -400,27 +399,29 @@ __global__ void __launch_bounds__(NW * 32, 1) lstm_tc_bwd_kernel(BwdP p) {
                 da[3] = dht * tc * og * (1.f - og);
                 dc = dct * fg;
             }
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                const __nv_bfloat16 v = __float2bfloat16(da[g]);
-                sg[(bb * 4 + g) * UPC + w] = v;
-                sx[(bb * UPC + w) * 4 + g] = v;
-            }
-        }
-        __syncthreads();
-        if (tid < NB * 4) {   // 16-byte stores
-            const int b = tid >> 2, c = tid & 3;
-            const int jb = js * JS + rs * UPC;
-            // exchange buffer (unit-major): this CTA's 32 consecutive r' of batch row b, chunk c
-            *reinterpret_cast<uint4*>(gcur + (size_t)b * H4 + (size_t)jb * 4 + c * 8) =
-                *reinterpret_cast<const uint4*>(sx + (b * UPC) * 4 + c * 8);
-            // dG_t for the weight-gradient GEMMs (standard gate-major layout): gate c, 8 consecutive units
-            if (b < B) *reinterpret_cast<uint4*>(p.dg16 + ((size_t)b * T + t) * H4 + (size_t)c * H + jb) =
-                *reinterpret_cast<const uint4*>(sg + (b * 4 + c) * UPC);
+            // exchange buffer (unit-major, r' = 4*j + g): the four gates of (unit j, batch row bb) are 8
+            // contiguous bytes -> ONE direct store per thread, no staging and no extra block barrier on the
+            // critical path (rows bb >= B carry zeros)
+            __nv_bfloat162 lo = __floats2bfloat162_rn(da[0], da[1]), hi = __floats2bfloat162_rn(da[2], da[3]);
+            uint2 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&lo);
+            pk.y = *reinterpret_cast<uint32_t*>(&hi);
+            *reinterpret_cast<uint2*>(gcur + (size_t)bb * H4 + (size_t)j * 4) = pk;
+            // gate-major staging for dG_t (weight-gradient GEMMs), stored after the barrier arrival
+            sg[(bb * 4 + 0) * UPC + w] = __low2bfloat16(lo);
+            sg[(bb * 4 + 1) * UPC + w] = __high2bfloat16(lo);
+            sg[(bb * 4 + 2) * UPC + w] = __low2bfloat16(hi);
+            sg[(bb * 4 + 3) * UPC + w] = __high2bfloat16(hi);
         }
         __syncthreads();
         ++epoch;
         if (tid == 0) { __threadfence(); atomicAdd(p.bar, 1u); }
+        if (tid < NB * 4) {   // off the critical path: dG_t in the standard gate-major layout, 16-byte stores
+            const int b = tid >> 2, c = tid & 3;
+            const int jb = js * JS + rs * UPC;
+            if (b < B) *reinterpret_cast<uint4*>(p.dg16 + ((size_t)b * T + t) * H4 + (size_t)c * H + jb) =
+                *reinterpret_cast<const uint4*>(sg + (b * 4 + c) * UPC);
+        }
         EB_PREFETCH(t - 1)                                   // overlaps the wait
         if (tid == 0) spin_wait_ge(p.bar, epoch * ncta);     // one poller per CTA (see forward kernel)
         __syncthreads();
@@ -509,7 +510,7 @@ template <int CS>
 size_t bwd_smem(int H) {
     static int pad = -1;
     if (pad < 0) { const char* e = getenv("EDGEDICT_LSTM_PADSMEM_BWD"); pad = e ? atoi(e) * 1024 : 0; }   // placement experiments
-    return (size_t)pad + (size_t)NB * (4 * H / CS + PAD) * 2 + sizeof(float) * (NW * (CS / 2) * 16 * 32 + 2 * 8 * CS * NB) + 2 * NB * 4 * UPC * 2 +
+    return (size_t)pad + (size_t)NB * (4 * H / CS + PAD) * 2 + sizeof(float) * (NW * (CS / 2) * 16 * 32 + 2 * 8 * CS * NB) + NB * 4 * UPC * 2 +
            sizeof(float) * 4 * NW * 32;
 }
 
