@@ -45,6 +45,9 @@ SIGNATURES = {
     "eb_transpose_to_bf16": (I, [P, I, P, L, L, P]),
     "eb_adam_step": (I, [P, P, P, P, L, F, F, F, F, F, I, F, P]),
     "eb_sumsq": (I, [P, L, P, P]),
+    "eb_fe_preemph_pad": (I, [P, P, I, I, L, I, F, I, P]),
+    "eb_fe_power": (I, [P, P, L, I, P]),
+    "eb_fe_log_stack": (I, [P, P, I, I, I, I, I, I, I, I, P]),
     # warp-transducer compatible ABI (include/rnnt.h)
     "get_warprnnt_version": (I, []),
     "rnntGetStatusString": (C.c_char_p, [I]),

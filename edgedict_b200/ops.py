@@ -44,14 +44,34 @@ class _Prof:
     def reset(self):
         self.events, self.launches = [], 0
 
-    def summary(self):
-        out = {}
+    def summary(self, base=None):
+        """Per-name totals.  `ms` is the UNION of the call intervals (calls of one name overlap when two layers'
+        kernels run on two streams in the wavefront schedule) when a `base` event recorded before the first call
+        is given, else their sum; `ms_sum` is always the plain sum."""
+        out, spans = {}, {}
         for name, a, b, nbytes, flops in self.events:
-            d = out.setdefault(name, dict(ms=0.0, calls=0, bytes=0.0, flops=0.0))
-            d["ms"] += a.elapsed_time(b)
+            d = out.setdefault(name, dict(ms=0.0, ms_sum=0.0, calls=0, bytes=0.0, flops=0.0))
+            d["ms_sum"] += a.elapsed_time(b)
             d["calls"] += 1
             d["bytes"] += nbytes
             d["flops"] += flops
+            if base is not None:
+                spans.setdefault(name, []).append((base.elapsed_time(a), base.elapsed_time(b)))
+        for name, d in out.items():
+            if base is None:
+                d["ms"] = d["ms_sum"]
+                continue
+            tot, cur_s, cur_e = 0.0, None, None
+            for s0, e0 in sorted(spans[name]):
+                if cur_e is None or s0 > cur_e:
+                    if cur_e is not None:
+                        tot += cur_e - cur_s
+                    cur_s, cur_e = s0, e0
+                else:
+                    cur_e = max(cur_e, e0)
+            if cur_e is not None:
+                tot += cur_e - cur_s
+            d["ms"] = tot
         return out
 
 
@@ -410,3 +430,32 @@ def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=
 
 def sumsq(x, out):
     check(lib().eb_sumsq(_p(x), x.numel(), _p(out), _s()), "eb_sumsq")
+
+
+# ---- log-mel front end ------------------------------------------------------------
+def logmel_frontend(x, basis, fbT, n_fft, hop, n_mels, n_stack, preemph, take_log=True, pad_to_divisible=True):
+    """x [B, L] fp32 waveform -> [B, T, n_mels*n_stack] log-mel features (see csrc/frontend.cu).
+    basis [n_fft, 2*nbins] = window * (cos | -sin); fbT [nbins, n_mels]."""
+    _need(x, f32, "x")
+    B, L = x.shape
+    nb = n_fft // 2 + 1
+    pad = n_fft // 2
+    R = -(-(L + 2 * pad) // hop)                       # frame slots per utterance (>= the 1 + L//hop real frames)
+    Lp = R * hop
+    F = 1 + L // hop
+    seq_len = -(-L // hop)
+    dev = x.device
+    xp = torch.zeros(B * Lp + n_fft, dtype=f32, device=dev)      # tail: the last slots' windows stay in bounds
+    check(lib().eb_fe_preemph_pad(_p(x), _p(xp), B, L, Lp, pad, float(preemph or 0.0), int(preemph is not None), _s()),
+          "eb_fe_preemph_pad")
+    rows = B * R
+    spec = gemm_f32(xp, hop, 1, basis, 2 * nb, 1, rows, 2 * nb, n_fft)
+    power = torch.empty(rows, nb, dtype=f32, device=dev)
+    check(lib().eb_fe_power(_p(spec), _p(power), rows, nb, _s()), "eb_fe_power")
+    mel = gemm_f32(power, nb, 1, fbT, n_mels, 1, rows, n_mels, nb)
+    Fs = F if pad_to_divisible else F - F % n_stack
+    T = -(-Fs // n_stack)
+    out = torch.empty(B, T, n_mels * n_stack, dtype=f32, device=dev)
+    check(lib().eb_fe_log_stack(_p(mel), _p(out), B, R, Fs, seq_len, n_mels, n_stack, T, int(take_log), _s()),
+          "eb_fe_log_stack")
+    return out

@@ -145,6 +145,22 @@ int eb_adam_step(float* p, const float* g, float* m, float* v, long n, float lr,
                  float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
 int eb_sumsq(const float* x, long n, float* out_accum, void* stream);
 
+/* ---- log-mel front end (the step before the path) ------------------------------
+ * replaces FilterbankFeatures.forward (rnnt/features.py:126-164) + Downsample (rnnt/transforms.py:37-51).
+ * eb_fe_preemph_pad : x[B,L] -> xp[B,Lp]: pre-emphasis (features.py:137-141) and the reflect padding of
+ *                     torch.stft(center=True) by `pad` = n_fft/2 samples; positions >= L+2*pad are zero.  With Lp a
+ *                     multiple of hop, frame g = b*(Lp/hop)+f starts at flat offset g*hop, so the STFT is
+ *                     eb_gemm_f32 on a strided view (sam = hop) against the windowed DFT basis [n_fft, 2*nbins].
+ * eb_fe_power       : spec[rows, re(nbins) | im(nbins)] -> power[rows, nbins]  (features.py:149)
+ * eb_fe_log_stack   : mel[B*rows_per_utt, n_mels] -> out[B, t_out, n_mels*n_stack]: log(x + 1e-20)
+ *                     (features.py:155-156), zero for frames >= seq_len (features.py:160-164) and for the
+ *                     stacking pad (transforms.py:41-45); out is the [B,T,F] layout Encoder.forward takes. */
+int eb_fe_preemph_pad(const float* x, float* xp, int B, int L, long Lp, int pad, float preemph,
+                      int use_preemph, void* stream);
+int eb_fe_power(const float* spec, float* power, long rows, int nbins, void* stream);
+int eb_fe_log_stack(const float* mel, float* out, int B, int rows_per_utt, int n_frames, int seq_len,
+                    int n_mels, int n_stack, int t_out, int take_log, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
