@@ -103,6 +103,82 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
     }
 }
 
+// Fused backward for H % 128 == 0, H <= 1024: ONE pass over dy / x / res produces dz AND the parameter gradients
+// (the two-kernel version above re-reads the three inputs for dgamma/dbeta and issues 4-byte accesses: it ran
+// at 1.9 TB/s).  128-bit accesses, NV float4 per lane; dgamma/dbeta partials live in registers across the rows
+// of a warp, are combined per CTA in shared memory and leave with one global atomic per column and CTA.
+constexpr int LNB_WARPS = 4;
+template <int NV>
+__global__ void __launch_bounds__(LNB_WARPS * 32)
+layernorm_bwd_fused_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ res,
+                           const float* __restrict__ gamma, const float* __restrict__ mean,
+                           const float* __restrict__ rstd, float* __restrict__ dz, float* __restrict__ dgamma,
+                           float* __restrict__ dbeta, long rows, int H) {
+    extern __shared__ float lnb_acc[];                       // [2][H]
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int H4 = H >> 2;
+    const long wstride = (long)gridDim.x * LNB_WARPS;
+    const float inv_h = 1.f / (float)H;
+    float4 ag[NV], ab[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { ag[i] = make_float4(0.f, 0.f, 0.f, 0.f); ab[i] = ag[i]; }
+    const float4* g4 = reinterpret_cast<const float4*>(gamma);
+    for (long r = (long)blockIdx.x * LNB_WARPS + w; r < rows; r += wstride) {
+        const float mu = mean[r], rs = rstd[r];
+        const float4* dy4 = reinterpret_cast<const float4*>(dy + r * H);
+        const float4* x4 = reinterpret_cast<const float4*>(x + r * H);
+        const float4* r4 = res ? reinterpret_cast<const float4*>(res + r * H) : nullptr;
+        float4 d[NV], xh[NV];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = lane + i * 32;
+            d[i] = make_float4(0.f, 0.f, 0.f, 0.f); xh[i] = d[i];
+            if (c < H4) {
+                d[i] = dy4[c];
+                float4 z = x4[c];
+                if (r4) { const float4 q = r4[c]; z.x += q.x; z.y += q.y; z.z += q.z; z.w += q.w; }
+                xh[i] = make_float4((z.x - mu) * rs, (z.y - mu) * rs, (z.z - mu) * rs, (z.w - mu) * rs);
+                const float4 gm = __ldg(g4 + c);
+                const float4 g = make_float4(d[i].x * gm.x, d[i].y * gm.y, d[i].z * gm.z, d[i].w * gm.w);
+                s1 += (g.x + g.y) + (g.z + g.w);
+                s2 += (g.x * xh[i].x + g.y * xh[i].y) + (g.z * xh[i].z + g.w * xh[i].w);
+                ag[i].x += d[i].x * xh[i].x; ag[i].y += d[i].y * xh[i].y; ag[i].z += d[i].z * xh[i].z; ag[i].w += d[i].w * xh[i].w;
+                ab[i].x += d[i].x; ab[i].y += d[i].y; ab[i].z += d[i].z; ab[i].w += d[i].w;
+            }
+        }
+        s1 = warp_sum(s1) * inv_h;
+        s2 = warp_sum(s2) * inv_h;
+        float4* dz4 = reinterpret_cast<float4*>(dz + r * H);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = lane + i * 32;
+            if (c < H4) {
+                const float4 gm = __ldg(g4 + c);
+                dz4[c] = make_float4(rs * (d[i].x * gm.x - s1 - xh[i].x * s2), rs * (d[i].y * gm.y - s1 - xh[i].y * s2),
+                                     rs * (d[i].z * gm.z - s1 - xh[i].z * s2), rs * (d[i].w * gm.w - s1 - xh[i].w * s2));
+            }
+        }
+    }
+    for (int c = threadIdx.x; c < 2 * H; c += blockDim.x) lnb_acc[c] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (lane + i * 32) * 4;
+        if (c < H) {
+            atomicAdd(lnb_acc + c, ag[i].x); atomicAdd(lnb_acc + c + 1, ag[i].y);
+            atomicAdd(lnb_acc + c + 2, ag[i].z); atomicAdd(lnb_acc + c + 3, ag[i].w);
+            atomicAdd(lnb_acc + H + c, ab[i].x); atomicAdd(lnb_acc + H + c + 1, ab[i].y);
+            atomicAdd(lnb_acc + H + c + 2, ab[i].z); atomicAdd(lnb_acc + H + c + 3, ab[i].w);
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < H; c += blockDim.x) {
+        atomicAdd(dgamma + c, lnb_acc[c]);
+        atomicAdd(dbeta + c, lnb_acc[H + c]);
+    }
+}
+
 // dgamma[c] += sum_r dy*xhat ; dbeta[c] += sum_r dy   (thread per column, rows chunked over grid.y)
 __global__ void layernorm_param_grad_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                             const float* __restrict__ res,
@@ -471,6 +547,21 @@ EB_API int eb_layernorm_bwd(const float* dy, const float* x, const float* res, c
                             float* dbeta, long rows, int H, void* stream) {
     if (!dy || !x || !gamma || !mean || !rstd || !dz || !dgamma || !dbeta || H > 2048)
         return EB_ERR_INVALID;
+    const bool vec_ok = H % 128 == 0 && H <= 1024 && rows > 0 &&
+                        ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dz) |
+                          reinterpret_cast<uintptr_t>(gamma) | (res ? reinterpret_cast<uintptr_t>(res) : 0)) & 15) == 0;
+    if (vec_ok) {
+        long blocks_f = (rows + LNB_WARPS - 1) / LNB_WARPS;
+        long cap_f = (long)eb_num_sms() * 3;
+        const int grid_f = (int)(blocks_f < cap_f ? blocks_f : cap_f);
+        const size_t sm = sizeof(float) * 2 * (size_t)H;
+#define LN_BWDF(NV) layernorm_bwd_fused_kernel<NV><<<grid_f, LNB_WARPS * 32, sm, ST(stream)>>>( \
+        dy, x, res, gamma, mean, rstd, dz, dgamma, dbeta, rows, H)
+        if (H <= 128) LN_BWDF(1); else if (H <= 256) LN_BWDF(2); else if (H <= 512) LN_BWDF(4); else LN_BWDF(8);
+#undef LN_BWDF
+        EB_CHECK_LAUNCH();
+        return EB_OK;
+    }
     long blocks = (rows + LN_WARPS - 1) / LN_WARPS;
     long cap = (long)eb_num_sms() * 8;
     int grid = (int)(blocks < cap ? blocks : cap);
@@ -572,7 +663,7 @@ EB_API int eb_colsum(const void* x, int x_bf16, float* out, long rows, int N, vo
     dim3 grid((N + 127) / 128, (unsigned)((rows + rpb - 1) / rpb));
     if (x_bf16 && N % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
         long rpb2 = (rows + 1023) / 1024;
-        if (rpb2 < 32) rpb2 = 32;
+        if (rpb2 < 128) rpb2 = 128;             // >= 128 rows per CTA: the per-CTA column atomics stay off the profile
         const int nth = (N / 8 < 128) ? N / 8 : 128;
         dim3 g2((N / 8 + nth - 1) / nth, (unsigned)((rows + rpb2 - 1) / rpb2));
         colsum_bf16_vec_kernel<<<g2, nth, 0, ST(stream)>>>((const __nv_bfloat16*)x, out, rows, N, rpb2);

@@ -71,7 +71,8 @@ def test_gemm_bf16_persistent_many_tiles():
     assert rel_err(y.cpu(), ref) < 2e-5
 
 
-@pytest.mark.parametrize("rows,H,res", [(7, 12, False), (33, 240, False), (64, 320, True), (19, 1024, True), (5, 1500, True)])
+@pytest.mark.parametrize("rows,H,res", [(7, 12, False), (33, 240, False), (64, 320, True), (19, 1024, True), (5, 1500, True),
+                                        (300, 256, False), (2000, 512, True), (4100, 1024, False), (3, 128, True)])
 def test_layernorm_fwd_bwd(rows, H, res):
     from edgedict_b200 import ops
     x, r = _r(rows, H, seed=1), (_r(rows, H, seed=2) if res else None)
