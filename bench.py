@@ -227,11 +227,14 @@ def run_ours(args):
     # the BASELINE.json side metric: joint+loss HBM fraction on the algorithmic bytes of SURVEY 8(d)
     n_logits = B * (T // 2) * (U + 1) * V
     if "joint_logits_lse" in kern:
-        # fused bf16 path: logits written once (bf16) by the joint GEMM epilogue, which also produces the
-        # denominators; gradient pass reads and rewrites them: 3*s*N with s = 2, GEMM inside the region
+        # fused bf16 path, joint GEMM inside the region: SURVEY 8(d) counts 4*s*N with the GEMM included (logits
+        # written by the epilogue, read for the denominators, read + gradient written by the gradient pass), s = 2
+        # for the bf16 logits this path materialises.  The denominators come out of the GEMM epilogue, so the
+        # kernels actually move 3*s*N; the achieved figure is still algorithmic bytes / time.
         jl_keys = ("joint_logits_lse", "rnnt_loss_fwd", "rnnt_loss_bwd")
-        jl_bytes = 3 * 2 * n_logits
-        note = "s=2 (bf16 logits), joint GEMM + lattice + gradient; denominators come out of the GEMM epilogue"
+        jl_bytes = 4 * 2 * n_logits
+        note = ("s=2 (bf16 logits), joint GEMM + lattice + in-place gradient; algorithmic 4*s*N (GEMM included), moved "
+                "3*s*N: the softmax statistics come out of the GEMM epilogue")
     else:
         jl_keys = hbm_kernels
         jl_bytes = (4 + 4 + (2 if args.precision == "bf16" else 4)) * n_logits
@@ -247,7 +250,7 @@ def run_ours(args):
                config=dict(workload="E6D2 (6x1024 LSTM enc / 2x256 pred / joint 640 / V=1024) fwd+loss+bwd+Adam, "
                                     "B=32/GPU T=1000 U=128 (configs[1]); frame=37.5 ms",
                            global_batch=B * world, seq_len=T, parallelism="dp%d" % world,
-                           l2="inputs >> L2: 8.45 GB of logits streamed per step"),
+                           l2="inputs >> L2: 4.2 GB of bf16 logits (8.45 GB with EDGEDICT_FUSE_LSE=0) streamed per step"),
                e2e=dict(value=round(audio / ms_e2e * 1e3, 1), unit="audio-sec/sec",
                         h2d_bytes_per_step=hx.numel() * 4 + hy.numel() * 4, d2h_bytes_per_step=4,
                         ms_per_step=round(ms_e2e, 3), host_ms_per_iteration=step_wall),

@@ -291,27 +291,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 }
                 if (LSE) {      // add the bias here (the statistics are over logits = acc + b2), then online softmax
                     const int col0 = n0 + c * 32;
+                    constexpr float LOG2E = 1.4426950408889634f;
                     float cm = -INFINITY;
+                    if (col0 + 32 <= N && bias_vec) {             // whole chunk inside the vocabulary: no per-element guards
 #pragma unroll
-                    for (int i4 = 0; i4 < 8; ++i4) {
-                        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (bias) {
-                            if (col0 + i4 * 4 + 3 < N) b4 = __ldg(reinterpret_cast<const float4*>(bias + col0 + i4 * 4));
+                        for (int i4 = 0; i4 < 8; ++i4) {
+                            const float4 b4 = bias ? __ldg(reinterpret_cast<const float4*>(bias + col0 + i4 * 4))
+                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+                            const float v0 = __uint_as_float(r[i4 * 4]) + b4.x, v1 = __uint_as_float(r[i4 * 4 + 1]) + b4.y;
+                            const float v2 = __uint_as_float(r[i4 * 4 + 2]) + b4.z, v3 = __uint_as_float(r[i4 * 4 + 3]) + b4.w;
+                            r[i4 * 4] = __float_as_uint(v0); r[i4 * 4 + 1] = __float_as_uint(v1);
+                            r[i4 * 4 + 2] = __float_as_uint(v2); r[i4 * 4 + 3] = __float_as_uint(v3);
+                            cm = fmaxf(fmaxf(cm, fmaxf(v0, v1)), fmaxf(v2, v3));
                         }
-                        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+                    } else {
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            float v = __uint_as_float(r[i4 * 4 + e]) + bb[e];
-                            if (col0 + i4 * 4 + e >= N) v = -INFINITY;
-                            r[i4 * 4 + e] = __float_as_uint(v);
+                        for (int i = 0; i < 32; ++i) {
+                            float v = __uint_as_float(r[i]) + ((bias && col0 + i < N) ? __ldg(bias + col0 + i) : 0.f);
+                            if (col0 + i >= N) v = -INFINITY;
+                            r[i] = __float_as_uint(v);
                             cm = fmaxf(cm, v);
                         }
                     }
                     const float nm = fmaxf(rm, cm);
-                    float a = 0.f;
+                    const float nml = nm * LOG2E;
+                    float a0 = 0.f, a1 = 0.f;                     // exp(v - nm) = ex2(v*log2e - nm*log2e): FFMA + MUFU + FADD
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) a += __expf(__uint_as_float(r[i]) - nm);
-                    rs = rs * __expf(rm - nm) + a;
+                    for (int i = 0; i < 32; i += 2) {
+                        a0 += fast_ex2(fmaf(__uint_as_float(r[i]), LOG2E, -nml));
+                        a1 += fast_ex2(fmaf(__uint_as_float(r[i + 1]), LOG2E, -nml));
+                    }
+                    rs = rs * fast_ex2((rm - nm) * LOG2E) + (a0 + a1);
                     rm = nm;
                 }
 #pragma unroll
@@ -344,6 +354,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
                                  : "=f"(vv[rr].x), "=f"(vv[rr].y), "=f"(vv[rr].z), "=f"(vv[rr].w)
                                  : "r"(sbuf + (uint32_t)((rr * 4 + rsub) * 36 + c4 * 4) * 4));
+                if (full && ksplit == 1 && !accumulate) {         // the common case, free of per-store mode tests
+                    if (c_bf16) {
+#pragma unroll
+                        for (int rr = 0; rr < 8; ++rr) {
+                            const float4 v = vv[rr];
+                            __nv_bfloat162 p0 = __floats2bfloat162_rn(v.x + bv.x, v.y + bv.y);
+                            __nv_bfloat162 p1 = __floats2bfloat162_rn(v.z + bv.z, v.w + bv.w);
+                            uint2 o;
+                            o.x = *reinterpret_cast<uint32_t*>(&p0);
+                            o.y = *reinterpret_cast<uint32_t*>(&p1);
+                            *reinterpret_cast<uint2*>(Ch + (row0 + rr * 4) * N + col) = o;
+                        }
+                    } else {
+#pragma unroll
+                        for (int rr = 0; rr < 8; ++rr) {
+                            const float4 v = vv[rr];
+                            *reinterpret_cast<float4*>(Cf + (row0 + rr * 4) * N + col) =
+                                make_float4(v.x + bv.x, v.y + bv.y, v.z + bv.z, v.w + bv.w);
+                        }
+                    }
+                } else
 #pragma unroll
                 for (int rr = 0; rr < 8; ++rr) {
                     float4 v = vv[rr];
@@ -395,12 +426,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 }
                 __syncwarp();
             }
-            if (LSE && nb == num_n - 1 && cell_ok) {              // whole vocabulary seen: publish the row statistics
-                const long cell = m0 + q * 32 + lane;
-                const float d = -(rm + logf(rs));
-                lse.denom[cell] = d;
-                lse.lpb[cell] = d + xb;
-                lse.lpl[cell] = d + xl;
+            if (LSE && nb == num_n - 1) {                         // whole vocabulary seen: publish the row statistics
+                if (EPW_ == 8) {
+                    // the two warps of a TMEM quadrant saw alternate 32-column chunks: merge their running
+                    // (max, sum, x_blank, x_label) through the staging tile of the second one
+                    const uint32_t sb2 = smem_u32(epi) + (uint32_t)((warp - 2) | 4) * EPI_WARP_BYTES;
+                    if (chalf == 1)
+                        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(sb2 + (uint32_t)lane * 16), "f"(rm), "f"(rs),
+                                     "f"(xb), "f"(xl) : "memory");
+                    asm volatile("bar.sync %0, 64;" :: "r"(1 + q) : "memory");
+                    if (chalf == 0) {
+                        float m2, s2, b2v, l2v;
+                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(m2), "=f"(s2), "=f"(b2v), "=f"(l2v)
+                                     : "r"(sb2 + (uint32_t)lane * 16) : "memory");
+                        const float m = fmaxf(rm, m2);
+                        rs = rs * fast_ex2((rm - m) * 1.4426950408889634f) + s2 * fast_ex2((m2 - m) * 1.4426950408889634f);
+                        rm = m; xb += b2v; xl += l2v;
+                    }
+                    asm volatile("bar.sync %0, 64;" :: "r"(1 + q) : "memory");
+                }
+                if (cell_ok && (EPW_ != 8 || chalf == 0)) {
+                    const long cell = m0 + q * 32 + lane;
+                    const float d = -(rm + logf(rs));
+                    lse.denom[cell] = d;
+                    lse.lpb[cell] = d + xb;
+                    lse.lpl[cell] = d + xl;
+                }
             }
             tc_fence_before();
             if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
@@ -521,15 +572,16 @@ int launch_low(const CUtensorMap& ta, const CUtensorMap& tb, void* C, int c_bf16
 template <int BN_>
 int launch_lse(const CUtensorMap& ta, const CUtensorMap& tb, void* C, const float* bias, long M, int N, long K,
                const LseArgs& lse, cudaStream_t st) {
-    auto kern = gemm_tc_kernel<false, false, BN_, true>;
+    using C_ = Cfg<BN_, 8>;                                  // two epilogue warps per TMEM quadrant (see kernel)
+    auto kern = gemm_tc_kernel<false, false, BN_, true, 8>;
     static bool attr_done = false;
     if (!attr_done) {
-        EB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN_>::SMEM_BYTES));
+        EB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM_BYTES));
         attr_done = true;
     }
     const long num_m = (M + BM - 1) / BM;
     const int grid = (int)(num_m < eb_num_sms() ? num_m : eb_num_sms());
-    kern<<<grid, Cfg<BN_>::NTHREADS, Cfg<BN_>::SMEM_BYTES, st>>>(ta, tb, C, 1, bias, 0, M, N, K, 1, lse);
+    kern<<<grid, C_::NTHREADS, C_::SMEM_BYTES, st>>>(ta, tb, C, 1, bias, 0, M, N, K, 1, lse);
     EB_CHECK_LAUNCH();
     return EB_OK;
 }

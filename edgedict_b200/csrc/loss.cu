@@ -24,7 +24,7 @@ namespace {
 
 template <typename T> struct M;
 template <> struct M<float> {
-    static __device__ __forceinline__ float exp_fast(float x) { return __expf(x); }
+    static __device__ __forceinline__ float exp_fast(float x) { return fast_exp(x); }
     static __device__ __forceinline__ float exp_acc(float x) { return expf(x); }
     static __device__ __forceinline__ float log_acc(float x) { return logf(x); }
     static __device__ __forceinline__ float log1p_acc(float x) { return log1pf(x); }
@@ -331,6 +331,82 @@ rnnt_grad_kernel(const TI* logits, TO* grads, const int* __restrict__ labels,
     }
 }
 
+// bf16 logits -> bf16 gradients (in place allowed), the fused-joint path: 8 values per lane and iteration
+// (one 16-byte load, one 16-byte store); the rare blank / label corrections are applied outside the unrolled
+// exponentials.  Same arithmetic as rnnt_grad_kernel (gpu_rnnt_kernel.h:143-179).
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+rnnt_grad_bf16x8_kernel(const __nv_bfloat16* logits, __nv_bfloat16* grads, const int* __restrict__ labels,
+                        const int* __restrict__ xlen, const int* __restrict__ ylen, const float* __restrict__ denom,
+                        const float* __restrict__ alphas, const float* __restrict__ betas,
+                        const float* __restrict__ ll_fwd, const float* __restrict__ gscale, int gscale_per_batch,
+                        float hscale, int B, int maxT, int maxU, int V, int blank) {
+    const int lane = threadIdx.x & 31;
+    const long ncells = (long)B * maxT * maxU;
+    const long wstride = (long)gridDim.x * WARPS;
+    for (long cell = (long)blockIdx.x * WARPS + (threadIdx.x >> 5); cell < ncells; cell += wstride) {
+        const int u = (int)(cell % maxU);
+        const long bt = cell / maxU;
+        const int t = (int)(bt % maxT);
+        const int b = (int)(bt / maxT);
+        const int Tn = xlen[b], Un = ylen[b] + 1;
+        const __nv_bfloat16* row = logits + cell * (long)V;
+        __nv_bfloat16* orow = grads + cell * (long)V;
+        if (t >= Tn || u >= Un) {
+            for (int v = lane * 8; v < V; v += 256) *reinterpret_cast<uint4*>(orow + v) = make_uint4(0u, 0u, 0u, 0u);
+            continue;
+        }
+        const float sc = hscale * (gscale ? gscale[gscale_per_batch ? b : 0] : 1.f);
+        const float a = alphas[cell], bt_ = betas[cell], ll = ll_fwd[b], d = denom[cell];
+        const int lab = (u < Un - 1) ? labels[b * (maxU - 1) + u] : -1;
+        const float c_all = a + bt_ - ll + d;
+        float c_blank = -INFINITY;
+        if (t < Tn - 1) c_blank = a - ll + d + betas[cell + maxU];
+        else if (u == Un - 1) c_blank = a - ll + d;
+        const float c_lab = (lab >= 0) ? a - ll + d + betas[cell + 1] : -INFINITY;
+        constexpr float LOG2E = 1.4426950408889634f;
+        const float c2 = c_all * LOG2E;
+        // logits and grads may be the same buffer: all four 16-byte loads of a group are issued before the first
+        // store, otherwise the possible aliasing serialises load -> store -> load and one row costs four DRAM
+        // round trips
+        for (int v0 = lane * 8; v0 < V; v0 += 1024) {
+            uint4 qq[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (v0 + k * 256 < V) qq[k] = *reinterpret_cast<const uint4*>(row + v0 + k * 256);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int v = v0 + k * 256;
+                if (v >= V) break;
+                const uint32_t w[4] = {qq[k].x, qq[k].y, qq[k].z, qq[k].w};
+                float x[8], g[8];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+                    x[2 * i] = f.x; x[2 * i + 1] = f.y;
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) g[i] = fast_ex2(fmaf(x[i], LOG2E, c2));
+                const unsigned ib = (unsigned)(blank - v), il = (unsigned)(lab - v);
+                if (ib < 8u || il < 8u) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        if ((unsigned)i == ib) g[i] -= expf(c_blank + x[i]);
+                        if ((unsigned)i == il) g[i] -= expf(c_lab + x[i]);
+                    }
+                }
+                uint32_t ow[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    __nv_bfloat162 pk = __floats2bfloat162_rn(g[2 * i] * sc, g[2 * i + 1] * sc);
+                    ow[i] = *reinterpret_cast<uint32_t*>(&pk);
+                }
+                *reinterpret_cast<uint4*>(orow + v) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            }
+        }
+    }
+}
+
 template <typename T>
 struct Workspace {
     T *denom, *lpb, *lpl, *alphas, *betas, *ll_fwd, *ll_bwd;
@@ -563,7 +639,13 @@ EB_API int eb_rnnt_loss_bwd_bf16(const void* logits16, void* grads16, const int*
                      ((reinterpret_cast<uintptr_t>(grads16) & 7) == 0);
     const __nv_bfloat16* in = reinterpret_cast<const __nv_bfloat16*>(logits16);
     __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(grads16);
-    if (vec)
+    const bool vec8 = (V % 8 == 0) && ((reinterpret_cast<uintptr_t>(logits16) & 15) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(grads16) & 15) == 0);
+    if (vec8)
+        rnnt_grad_bf16x8_kernel<WARPS><<<row_grid(ncells, WARPS), WARPS * 32, 0, st>>>(
+            in, out, labels, xlen, ylen, w.denom, w.alphas, w.betas, w.ll_fwd, gscale_dev, gscale_per_batch,
+            (float)host_scale, B, maxT, maxU, V, blank);
+    else if (vec)
         rnnt_grad_kernel<float, __nv_bfloat16, true, WARPS, __nv_bfloat16><<<row_grid(ncells, WARPS), WARPS * 32, 0, st>>>(
             in, out, labels, xlen, ylen, w.denom, w.alphas, w.betas, w.ll_fwd, gscale_dev, gscale_per_batch,
             (float)host_scale, B, maxT, maxU, V, blank);

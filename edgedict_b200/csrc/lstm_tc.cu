@@ -66,8 +66,8 @@ __device__ __forceinline__ uint32_t ldg_u32(const __nv_bfloat16* p) {
 }
 // bf16-mode gate nonlinearities: ex2.approx + rcp.approx (abs. error ~1e-7, far below the bf16
 // rounding of the exchanged h); the fp32 parity kernels in lstm.cu keep expf/tanhf.
-__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
-__device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); }
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + fast_exp(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.f, fast_exp(2.f * x) + 1.f); }
 
 // one warp copies its K-range (cpr 16-byte chunks per row, NB rows) of the exchange buffer into a
 // padded shared tile.  No integer division in the common case (cpr divides 32).

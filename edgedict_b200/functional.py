@@ -11,11 +11,11 @@ from . import ops
 import os
 
 f32, bf16 = torch.float32, torch.bfloat16
-# bf16 mode option: fuse the softmax statistics of the loss into the joint's output GEMM epilogue and keep
-# bf16 logits (EDGEDICT_FUSE_LSE=1).  Correct (tests/test_gpu_model.py) but measured SLOWER on B200
-# (9.6 ms vs 7.5 ms for joint+loss at E6D2): the one-warp-per-scheduler epilogue becomes the bottleneck of the
-# GEMM and the 8-byte-per-lane bf16 gradient pass streams at 3.4 TB/s instead of 5.5 -- off by default.
-FUSE_JOINT_LSE = os.environ.get("EDGEDICT_FUSE_LSE", "0") == "1"
+# bf16 mode: the joint's output GEMM also emits the softmax statistics of the loss from its fp32 TMEM accumulators
+# and writes bf16 logits; the 8 GB denominator pass disappears and the gradient pass runs in place on 4 GB
+# (EDGEDICT_FUSE_LSE=0 selects the unfused fp32-logits path).  Measured at E6D2: joint GEMM + loss 4.8 ms against
+# 7.2 ms unfused, once the epilogue used ex2.approx.ftz, unguarded full chunks and eight epilogue warps.
+FUSE_JOINT_LSE = os.environ.get("EDGEDICT_FUSE_LSE", "1") != "0"
 
 
 def _c(t):

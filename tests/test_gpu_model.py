@@ -179,7 +179,7 @@ def test_fused_joint_lse_path_matches_unfused_bf16_path(B, T, U, E, D, J, V):
         loss, costs = Fn.JointLoss.apply(*ins, labels.cuda(), xl.cuda(), yl.cuda(), 0, "bf16")
         loss.backward()
         res.append((loss.detach().cpu(), costs.cpu(), [t.grad.cpu() for t in ins]))
-    Fn.FUSE_JOINT_LSE = False
+    Fn.FUSE_JOINT_LSE = True
     (l0, c0, g0), (l1, c1, g1) = res
     assert rel_err(c1, c0) < 2e-3           # same bf16 operands; statistics from fp32 accumulators on both sides
     for a, b, name in zip(g1, g0, "h_enc h_dec w1 b1 w2 b2".split()):
