@@ -368,6 +368,29 @@ __global__ void joint_hidden_bwd_t_bf16_kernel(__nv_bfloat16* __restrict__ dh, c
         *reinterpret_cast<float4*>(o + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
     }
 }
+// dep[b,t,:] = sum_u dpre[b,t,u,:] for dpre already produced by the d-hidden GEMM epilogue (eb_gemm_bf16_dtanh)
+__global__ void joint_dep_reduce_bf16_kernel(const __nv_bfloat16* __restrict__ dpre, float* __restrict__ dep, int U, int J) {
+    const long bt = blockIdx.x;
+    const int J8 = J / 8;
+    for (int q = threadIdx.x; q < J8; q += blockDim.x) {
+        const __nv_bfloat16* g = dpre + bt * (long)U * J + q * 8;
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
+        for (int u = 0; u < U; ++u) {
+            const uint4 gv = *reinterpret_cast<const uint4*>(g + (long)u * J);
+            const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 gf = unpack_bf16(gw[i]);
+                acc[2 * i] += gf.x;
+                acc[2 * i + 1] += gf.y;
+            }
+        }
+        float* o = dep + bt * J + q * 8;
+        *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        *reinterpret_cast<float4*>(o + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+}
 // ddp[b,u,:] = sum_t dpre[b,t,u,:]   one CTA per (b,u)
 __global__ void joint_hidden_bwd_u_f32_kernel(const float* __restrict__ dpre, float* __restrict__ ddp, int T,
                                               int U, int J) {
@@ -652,6 +675,25 @@ EB_API int eb_joint_hidden_bwd(void* dhidden_inout, const void* hidden, int is_b
         EB_CHECK_LAUNCH();
         joint_hidden_bwd_u_f32_kernel<<<B * U, 256, 0, ST(stream)>>>((const float*)dhidden_inout, ddp, T, U, J);
     }
+    EB_CHECK_LAUNCH();
+    return EB_OK;
+}
+
+// The two broadcast reductions of the joint's first layer when d(pre-activation) [B,T,U,J] (bf16) already exists:
+// dep[b,t,:] = sum_u, ddp[b,u,:] = sum_t  (backward of the e_t + d_u broadcast add of Joint.forward).
+EB_API int eb_joint_dpre_reduce(const void* dpre16, float* dep, float* ddp, int B, int T, int U, int J, void* stream) {
+    if (!dpre16 || !dep || !ddp || B <= 0 || T <= 0 || U <= 0 || J <= 0 || J % 8 ||
+        (reinterpret_cast<uintptr_t>(dpre16) & 15) || (reinterpret_cast<uintptr_t>(dep) & 15))
+        return EB_ERR_INVALID;
+    joint_dep_reduce_bf16_kernel<<<B * T, 96, 0, ST(stream)>>>((const __nv_bfloat16*)dpre16, dep, U, J);
+    EB_CHECK_LAUNCH();
+    EB_CUDA(cudaMemsetAsync(ddp, 0, sizeof(float) * (size_t)B * U * J, ST(stream)));
+    int tsplit = (4 * eb_num_sms() + B * U - 1) / (B * U);
+    if (tsplit < 1) tsplit = 1;
+    if (tsplit > T) tsplit = T;
+    const int tchunk = (T + tsplit - 1) / tsplit;
+    joint_hidden_bwd_u_bf16_kernel<<<dim3(B * U, (T + tchunk - 1) / tchunk), 96, 0, ST(stream)>>>(
+        (const __nv_bfloat16*)dpre16, ddp, T, U, J, tchunk);
     EB_CHECK_LAUNCH();
     return EB_OK;
 }

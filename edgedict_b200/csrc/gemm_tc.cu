@@ -143,6 +143,9 @@ struct LseArgs {
     const int* labels; const int* xlen; const int* ylen;     // [B,maxU-1], [B], [B]
     float* denom; float* lpb; float* lpl;                     // [B*maxT*maxU] each (loss workspace)
     int maxT, maxU, blank;
+    // (not LSE) optional epilogue multiplier for bf16 outputs: C = (A B) * (1 - aux^2), aux bf16 [M,N] -- the tanh'
+    // of the joint's hidden layer applied where d hidden is produced (eb_gemm_bf16_dtanh)
+    const __nv_bfloat16* aux;
 };
 
 // A_MN / B_MN: operand stored with its M (resp. N) index contiguous ("MN-major"), else K contiguous.
@@ -355,7 +358,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                                  : "=f"(vv[rr].x), "=f"(vv[rr].y), "=f"(vv[rr].z), "=f"(vv[rr].w)
                                  : "r"(sbuf + (uint32_t)((rr * 4 + rsub) * 36 + c4 * 4) * 4));
                 if (full && ksplit == 1 && !accumulate) {         // the common case, free of per-store mode tests
-                    if (c_bf16) {
+                    if (c_bf16 && !LSE && lse.aux) {
+                        uint2 hq[8];
+#pragma unroll
+                        for (int rr = 0; rr < 8; ++rr)
+                            hq[rr] = __ldg(reinterpret_cast<const uint2*>(lse.aux + (row0 + rr * 4) * N + col));
+#pragma unroll
+                        for (int rr = 0; rr < 8; ++rr) {
+                            const float4 v = vv[rr];
+                            const float2 h0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hq[rr].x));
+                            const float2 h1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hq[rr].y));
+                            __nv_bfloat162 p0 = __floats2bfloat162_rn((v.x + bv.x) * (1.f - h0.x * h0.x), (v.y + bv.y) * (1.f - h0.y * h0.y));
+                            __nv_bfloat162 p1 = __floats2bfloat162_rn((v.z + bv.z) * (1.f - h1.x * h1.x), (v.w + bv.w) * (1.f - h1.y * h1.y));
+                            uint2 o;
+                            o.x = *reinterpret_cast<uint32_t*>(&p0);
+                            o.y = *reinterpret_cast<uint32_t*>(&p1);
+                            *reinterpret_cast<uint2*>(Ch + (row0 + rr * 4) * N + col) = o;
+                        }
+                    } else if (c_bf16) {
 #pragma unroll
                         for (int rr = 0; rr < 8; ++rr) {
                             const float4 v = vv[rr];
@@ -386,6 +406,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                             atomicAdd(cp, v.x); atomicAdd(cp + 1, v.y); atomicAdd(cp + 2, v.z); atomicAdd(cp + 3, v.w);
                         } else if (c_bf16) {
                             __nv_bfloat16* cp = Ch + row * N + col;
+                            if (!LSE && lse.aux) {
+                                const __nv_bfloat16* hp = lse.aux + row * N + col;
+                                const float h0 = __bfloat162float(hp[0]), h1 = __bfloat162float(hp[1]);
+                                const float h2 = __bfloat162float(hp[2]), h3 = __bfloat162float(hp[3]);
+                                v.x *= 1.f - h0 * h0; v.y *= 1.f - h1 * h1; v.z *= 1.f - h2 * h2; v.w *= 1.f - h3 * h3;
+                            }
                             if (accumulate) {
                                 const uint2 o = *reinterpret_cast<const uint2*>(cp);
                                 const float2 o0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&o.x));
@@ -414,6 +440,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                             if (ksplit > 1) atomicAdd(Cf + row * N + col + e, x);
                             else if (c_bf16) {
                                 __nv_bfloat16* cp = Ch + row * N + col + e;
+                                if (!LSE && lse.aux) { const float h = __bfloat162float(lse.aux[row * N + col + e]); x *= 1.f - h * h; }
                                 if (accumulate) x += __bfloat162float(*cp);
                                 *cp = __float2bfloat16(x);
                             } else {
@@ -499,7 +526,9 @@ bool make_map(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer,
 
 template <bool A_MN, bool B_MN, int BN_>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, void* C, int c_bf16, const float* bias, int accumulate,
-           long M, int N, long K, cudaStream_t st) {
+           long M, int N, long K, cudaStream_t st, const void* aux = nullptr) {
+    LseArgs ea = LseArgs();
+    ea.aux = reinterpret_cast<const __nv_bfloat16*>(aux);
     constexpr int BN = BN_;
     const long out_tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     const long nkb = (K + BK - 1) / BK;
@@ -538,7 +567,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, void* C, int c_bf16, co
             EB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN_, 8>::SMEM_BYTES));
             attr_done = true;
         }
-        kern<<<grid, Cfg<BN_, 8>::NTHREADS, Cfg<BN_, 8>::SMEM_BYTES, st>>>(ta, tb, C, c_bf16, bias, accumulate, M, N, K, ksplit, LseArgs());
+        kern<<<grid, Cfg<BN_, 8>::NTHREADS, Cfg<BN_, 8>::SMEM_BYTES, st>>>(ta, tb, C, c_bf16, bias, accumulate, M, N, K, ksplit, ea);
     } else {
         auto kern = gemm_tc_kernel<A_MN, B_MN, BN_, false, 4>;
         static bool attr_done = false;
@@ -546,7 +575,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, void* C, int c_bf16, co
             EB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN_, 4>::SMEM_BYTES));
             attr_done = true;
         }
-        kern<<<grid, Cfg<BN_, 4>::NTHREADS, Cfg<BN_, 4>::SMEM_BYTES, st>>>(ta, tb, C, c_bf16, bias, accumulate, M, N, K, ksplit, LseArgs());
+        kern<<<grid, Cfg<BN_, 4>::NTHREADS, Cfg<BN_, 4>::SMEM_BYTES, st>>>(ta, tb, C, c_bf16, bias, accumulate, M, N, K, ksplit, ea);
     }
     EB_CHECK_LAUNCH();
     return EB_OK;
@@ -621,8 +650,26 @@ EB_API int eb_gemm_bf16(const void* A, int a_mn_major, const void* B, int b_mn_m
     return eb_gemm_bf16_ex(A, a_mn_major, B, b_mn_major, C, c_bf16, bias, accumulate, M, N, K, 0, stream);
 }
 
+static int gemm_dispatch(const void* A, int a_mn_major, const void* B, int b_mn_major, void* C, int c_bf16,
+                         const float* bias, int accumulate, long M, int N, long K, int flags, const void* aux,
+                         void* stream);
+
 EB_API int eb_gemm_bf16_ex(const void* A, int a_mn_major, const void* B, int b_mn_major, void* C, int c_bf16,
                            const float* bias, int accumulate, long M, int N, long K, int flags, void* stream) {
+    return gemm_dispatch(A, a_mn_major, B, b_mn_major, C, c_bf16, bias, accumulate, M, N, K, flags, nullptr, stream);
+}
+
+// C16[M,N] = bf16( (A B) * (1 - hid16^2) ): the joint's d hidden GEMM with tanh' applied in the epilogue (Joint.forward's
+// Tanh, rnnt/models.py:164): d(pre-activation) leaves the GEMM directly, one pass over the 2.6 GB tensor less.
+EB_API int eb_gemm_bf16_dtanh(const void* A, int a_mn_major, const void* B, int b_mn_major, void* C16,
+                              const void* hid16, long M, int N, long K, void* stream) {
+    if (!hid16 || (reinterpret_cast<uintptr_t>(hid16) & 7) || (reinterpret_cast<uintptr_t>(C16) & 7) || N % 4) return EB_ERR_INVALID;
+    return gemm_dispatch(A, a_mn_major, B, b_mn_major, C16, 1, nullptr, 0, M, N, K, 0, hid16, stream);
+}
+
+static int gemm_dispatch(const void* A, int a_mn_major, const void* B, int b_mn_major, void* C, int c_bf16,
+                         const float* bias, int accumulate, long M, int N, long K, int flags, const void* aux,
+                         void* stream) {
     if (!A || !B || !C || M <= 0 || N <= 0 || K <= 0) return EB_ERR_INVALID;
     const bool low = (flags & EB_GEMM_CORESIDENT) != 0;
     if (low && (a_mn_major || b_mn_major)) return EB_ERR_INVALID;
@@ -648,8 +695,8 @@ EB_API int eb_gemm_bf16_ex(const void* A, int a_mn_major, const void* B, int b_m
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (low) return launch_low(ta, tb, C, c_bf16, bias, accumulate, M, N, K, st);
 #define EB_GO(AM, BMN)                                                                              \
-    return wide ? launch<AM, BMN, 256>(ta, tb, C, c_bf16, bias, accumulate, M, N, K, st)           \
-                : launch<AM, BMN, 128>(ta, tb, C, c_bf16, bias, accumulate, M, N, K, st)
+    return wide ? launch<AM, BMN, 256>(ta, tb, C, c_bf16, bias, accumulate, M, N, K, st, aux)      \
+                : launch<AM, BMN, 128>(ta, tb, C, c_bf16, bias, accumulate, M, N, K, st, aux)
     if (a_mn_major) {
         if (b_mn_major) { EB_GO(true, true); }
         EB_GO(true, false);

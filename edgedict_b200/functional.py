@@ -396,8 +396,13 @@ def _joint_bwd(ctx_p, dlog2, hid, he2, hd2, w1, w2, dims, db2=None):
         dw2 = ops.mm_tn(hid2, dl16, p, dy16=hid2, x16=dl16).t().contiguous()
     else:
         dw2 = ops.mm_tn(dlog2, hid2, p, dy16=dl16, x16=hid2 if p == "bf16" else None)
-    dhid = ops.mm_nn(dlog2, w2, p, dy16=dl16, out_bf16=(p == "bf16"))
-    dep, ddp = ops.joint_hidden_bwd(dhid.view(B, T, U, J), hid)
+    if p == "bf16" and J % 8 == 0 and hid.dtype == bf16:
+        # tanh' applied in the d-hidden GEMM's epilogue: d(pre-activation) leaves the GEMM, then two pure reductions
+        dpre = ops.gemm_bf16_dtanh(dl16, ops.cast_bf16(w2.contiguous()), True, hid2, B * T * U, J, V)
+        dep, ddp = ops.joint_dpre_reduce(dpre.view(B, T, U, J))
+    else:
+        dhid = ops.mm_nn(dlog2, w2, p, dy16=dl16, out_bf16=(p == "bf16"))
+        dep, ddp = ops.joint_hidden_bwd(dhid.view(B, T, U, J), hid)
     dep2, ddp2 = dep.view(B * T, J), ddp.view(B * U, J)
     w1e, w1d = w1[:, :E], w1[:, E:]
     dhe = ops.mm_nn(dep2, w1e, p).view(B, T, E)

@@ -361,6 +361,25 @@ def joint_hidden_bwd(dhid, hid):
     return dep, ddp
 
 
+def gemm_bf16_dtanh(A16, B16, b_mn, hid16, M, N, K):
+    """bf16 [M,N] = (A16 [M,K] @ B) * (1 - hid16^2)  (B16: [N,K] if not b_mn else [K,N])."""
+    out = torch.empty(M, N, dtype=bf16, device=A16.device)
+    with _timed("gemm_bf16_n%s" % ("n" if b_mn else "t"), 1, 2.0 * (M * K + N * K) + 4.0 * M * N, 2.0 * M * N * K):
+        check(lib().eb_gemm_bf16_dtanh(_p(A16), 0, _p(B16), int(b_mn), _p(out), _p(hid16), M, N, K, _s()),
+              "eb_gemm_bf16_dtanh")
+    return out
+
+
+def joint_dpre_reduce(dpre16):
+    """dpre16 [B,T,U,J] bf16 -> (dep [B,T,J], ddp [B,U,J]) fp32."""
+    B, T, U, J = dpre16.shape
+    dep = torch.empty(B, T, J, dtype=f32, device=dpre16.device)
+    ddp = torch.empty(B, U, J, dtype=f32, device=dpre16.device)
+    check(lib().eb_joint_dpre_reduce(_p(dpre16), _p(dep), _p(ddp), B, T, U, J, _s()), "eb_joint_dpre_reduce")
+    PROF.launches += 1
+    return dep, ddp
+
+
 def rnnt_workspace(B, T, U, dtype, device):
     n = lib().eb_rnnt_workspace_bytes(B, T, U, 8 if dtype == torch.float64 else 4)
     return torch.empty(n, dtype=torch.uint8, device=device)

@@ -63,6 +63,11 @@ int eb_gemm_bf16(const void* A, int a_mn_major, const void* B, int b_mn_major, v
 int eb_gemm_bf16_ex(const void* A, int a_mn_major, const void* B, int b_mn_major, void* C, int c_bf16,
                     const float* bias, int accumulate, long M, int N, long K, int flags, void* stream);
 
+/* C16[M,N] = bf16((A B) * (1 - hid16[M,N]^2)): the joint's d-hidden GEMM with the derivative of Joint.forward's Tanh
+ * (rnnt/models.py:164) applied in the epilogue, so that d(pre-activation) leaves the GEMM directly. */
+int eb_gemm_bf16_dtanh(const void* A, int a_mn_major, const void* B, int b_mn_major, void* C16, const void* hid16,
+                       long M, int N, long K, void* stream);
+
 /* joint output layer + softmax statistics in one GEMM (bf16 mode): replaces the second Linear of Joint
  * (rnnt/models.py:165) together with reduce_max/reduce_exp (warp-transducer reduce.h:45-104) and the
  * blank/label gathers of the lattice kernels.  denom/lpb/lpl: the first three arrays of the loss workspace. */
@@ -118,6 +123,8 @@ int eb_joint_hidden_fwd(const float* ep, const float* dp, void* hidden, int hidd
                         int U, int J, void* stream);
 int eb_joint_hidden_bwd(void* dhidden_inout, const void* hidden, int is_bf16, float* dep, float* ddp,
                         int B, int T, int U, int J, void* stream);
+/* the same two reductions when d(pre-activation) [B,T,U,J] bf16 is already available (eb_gemm_bf16_dtanh) */
+int eb_joint_dpre_reduce(const void* dpre16, float* dep, float* ddp, int B, int T, int U, int J, void* stream);
 
 /* ---- streaming greedy decode: one persistent kernel per audio chunk -----------------------------
  * replaces PytorchStreamDecoder.decode's Python loop (rnnt/stream.py:93-120).  The host builds a

@@ -214,3 +214,22 @@ def test_lstm_tensor_core_layer_vs_oracle(B, T, I, H):
     ((yd * dy.cuda()).sum() + (hTd * dh.cuda()).sum() + (cTd * dc.cuda()).sum()).backward()
     for name, a, r in zip("x h0 c0 w_ih w_hh b_ih b_hh".split(), dev_in, ref_in):
         assert rel_err(a.grad.cpu(), r.grad) < 5e-2, name
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 128, 64), (1000, 640, 256), (257, 72, 96)])
+def test_gemm_dtanh_epilogue_and_dpre_reductions(M, N, K):
+    """eb_gemm_bf16_dtanh: (A B) * (1 - hid^2) in the GEMM epilogue (full and edge tiles), then eb_joint_dpre_reduce."""
+    from edgedict_b200 import ops
+    a = (_r(M, K, seed=1) / 4).bfloat16().cuda()
+    w = (_r(K, N, seed=2) / 4).bfloat16().cuda()
+    hid = torch.tanh(_r(M, N, seed=3)).bfloat16().cuda()
+    got = ops.gemm_bf16_dtanh(a, w, True, hid, M, N, K).float().cpu()
+    ref = (a.float().cpu() @ w.float().cpu()) * (1 - hid.float().cpu() ** 2)
+    assert rel_err(got, ref) < 1e-2                       # bf16 output rounding
+    if N % 8 == 0 and M % 4 == 0:
+        B, T = 2, 2
+        U = M // 4
+        d4 = got.bfloat16().cuda().view(B, T, U, N)
+        dep, ddp = ops.joint_dpre_reduce(d4)
+        assert rel_err(dep.cpu(), d4.float().cpu().sum(2)) < 1e-5
+        assert rel_err(ddp.cpu(), d4.float().cpu().sum(1)) < 1e-5
