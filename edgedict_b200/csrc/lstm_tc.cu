@@ -119,31 +119,15 @@ struct FwdP {
     __nv_bfloat16* hx;            // [2][NB][H] exchange
     unsigned* bar;
     int B, T, H;
-    int dbg;                      // timing experiments only (EDGEDICT_TC_DBG): 1 skip wait, 2 skip pull+mma,
-                                  // 4 skip non-critical stores, 8 single poller, 16 skip fence
 };
 
-// NBT = batch rows per CTA.  NBT = 16: the batch tile of 32 is split into two independent halves
-// (blockIdx.y) whose CTAs are co-resident two per SM -- two independent recurrences interleave on
-// every SM and hide each other's barrier / exchange latency (the per-step critical path is latency,
-// not throughput: ~1 of 4 issue slots is used).
-template <int NBT>
-__global__ void __launch_bounds__(NW * 32, (NBT == 16) ? 2 : EB_LSTM_MINB) lstm_tc_fwd_kernel(FwdP p) {
+// One batch tile of up to NBT = 32 rows per launch.  (Splitting the tile into two independent 16-row halves that
+// are co-resident on every SM was measured: no gain, each half is as latency-bound as the whole --
+// profiles/r1/lstm_pairing_experiments.txt.  Pairing DIFFERENT layers is what pays: functional.LSTMStack.)
+constexpr int NBT = NB;
+__global__ void __launch_bounds__(NW * 32, EB_LSTM_MINB) lstm_tc_fwd_kernel(FwdP p) {
     constexpr int NT = NBT / 8;                              // batch n-tiles
     constexpr int SL = NT * 8;                               // accumulator slots per thread
-    const int hb = blockIdx.y;                               // which batch tile
-    p.xg += (size_t)hb * NBT * p.T * 4 * p.H;
-    p.y += (size_t)hb * NBT * p.T * p.H;
-    if (p.y16) p.y16 += (size_t)hb * NBT * p.T * p.H;
-    if (p.gates) p.gates += (size_t)hb * NBT * p.T * 4 * p.H;
-    if (p.cseq) p.cseq += (size_t)hb * NBT * p.T * p.H;
-    if (p.h0) p.h0 += (size_t)hb * NBT * p.H;
-    if (p.c0) p.c0 += (size_t)hb * NBT * p.H;
-    p.hT += (size_t)hb * NBT * p.H;
-    p.cT += (size_t)hb * NBT * p.H;
-    p.hx += (size_t)hb * 2 * NBT * p.H;
-    p.bar += hb * 64;
-    p.B = min(NBT, p.B - hb * NBT);
     extern __shared__ __align__(16) unsigned char smraw[];
     const int H = p.H, B = p.B, T = p.T;
     const int HP = H + PAD;
@@ -203,17 +187,12 @@ __global__ void __launch_bounds__(NW * 32, (NBT == 16) ? 2 : EB_LSTM_MINB) lstm_
     for (int t = 0; t < T; ++t) {
         const __nv_bfloat16* hprev = p.hx + ((t + 1) & 1) * xstride;
         __nv_bfloat16* hnext = p.hx + (t & 1) * xstride;
-        if (!(p.dbg & 1)) {
-            // grid barrier, wait side: ONE poller per CTA (8 pollers per CTA cost ~1.1 us/step of L2
-            // contention on the counter line), then a block barrier
-            if (tid == 0) {
-                if (p.dbg & 1024) { const volatile unsigned* f = p.bar; while (*f < epoch * ncta) {} }
-                else spin_wait_ge(p.bar, epoch * ncta);
-            }
-            __syncthreads();
-        }
+        // grid barrier, wait side: ONE poller per CTA (8 pollers per CTA cost ~1.1 us/step of L2 contention on
+        // the counter line), then a block barrier
+        if (tid == 0) spin_wait_ge(p.bar, epoch * ncta);
+        __syncthreads();
         // pull this warp's K-range of h_{t-1}: NB rows x (myks*16) bf16
-        if (!(p.dbg & 2)) warp_pull(hs + ks0 * 16, HP, hprev + ks0 * 16, H, myks * 2, (p.dbg & 2048) ? NBT / 4 : NBT);
+        warp_pull(hs + ks0 * 16, HP, hprev + ks0 * 16, H, myks * 2, NBT);
         float acc[2][NT][4];
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
@@ -223,7 +202,7 @@ __global__ void __launch_bounds__(NW * 32, (NBT == 16) ? 2 : EB_LSTM_MINB) lstm_
                 for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
-            if (ks < myks && !(p.dbg & 2)) {
+            if (ks < myks) {
                 uint32_t b01[4], b23[4];
                 load_b<NT>(b01, b23, hs, HP, ks0 + ks);
 #pragma unroll
@@ -273,16 +252,11 @@ __global__ void __launch_bounds__(NW * 32, (NBT == 16) ? 2 : EB_LSTM_MINB) lstm_
         if (w == 0) {   // publish h_t: one 16-byte store per batch row, then a single fence + arrive
             if (l < NBT) *reinterpret_cast<uint4*>(hnext + (size_t)l * H + j0) = *reinterpret_cast<const uint4*>(sh_h + l * UPC);
             __syncwarp();
-            if (l == 0) {
-                if (p.dbg & 16) atomicAdd(p.bar, 1u);                                   // (unsafe reference point)
-                else if (p.dbg & 256) { asm volatile("fence.acq_rel.gpu;" ::: "memory"); atomicAdd(p.bar, 1u); }
-                else if (p.dbg & 512) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(p.bar) : "memory");
-                else { __threadfence(); atomicAdd(p.bar, 1u); }
-            }
+            if (l == 0) { __threadfence(); atomicAdd(p.bar, 1u); }
         }
         ++epoch;
         // everything below overlaps the other CTAs' progress towards the barrier
-        if (own && !(p.dbg & 4)) {
+        if (own) {
             p.y[oh] = hn;
             if (p.y16) p.y16[oh] = __float2bfloat16(hn);
             if (p.gates) { float* g_p = p.gates + og4; g_p[0] = ig; g_p[H] = fg; g_p[2 * (long)H] = gg; g_p[3 * (long)H] = og; }
@@ -508,9 +482,7 @@ inline bool tc_ok(int B, int H) { return H % 64 == 0 && H <= 1024 && B >= 1; }
 
 template <int CS>
 size_t bwd_smem(int H) {
-    static int pad = -1;
-    if (pad < 0) { const char* e = getenv("EDGEDICT_LSTM_PADSMEM_BWD"); pad = e ? atoi(e) * 1024 : 0; }   // placement experiments
-    return (size_t)pad + (size_t)NB * (4 * H / CS + PAD) * 2 + sizeof(float) * (NW * (CS / 2) * 16 * 32 + 2 * 8 * CS * NB) + NB * 4 * UPC * 2 +
+    return (size_t)NB * (4 * H / CS + PAD) * 2 + sizeof(float) * (NW * (CS / 2) * 16 * 32 + 2 * 8 * CS * NB) + NB * 4 * UPC * 2 +
            sizeof(float) * 4 * NW * 32;
 }
 
@@ -606,27 +578,9 @@ EB_API int eb_lstm_tc_fwd(const float* xg, const void* whh16, const float* h0, c
                           void* scratch, int B, int T, int H, void* stream) {
     if (!xg || !whh16 || !y || !hT || !cT || !scratch || T <= 0 || !tc_ok(B, H)) return EB_ERR_INVALID;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    // batch tile of 16 rows, two tiles co-resident per SM (see kernel comment), unless disabled or
-    // the occupancy query says two CTAs do not fit
-    static int split = -1;
-    if (split < 0) {
-        const char* e = getenv("EDGEDICT_LSTM_SPLIT");
-        split = e ? (atoi(e) ? 1 : 0) : 0;     // measured: no gain (each half is as latency-bound as the whole), off by default
-        if (split) {
-            int nblk = 0;
-            const size_t sm16 = (size_t)16 * (1024 + PAD) * 2 + sizeof(float) * NW * 16 * 32 + 16 * UPC * 2 + sizeof(float) * 4 * NW * 32;
-            cudaFuncSetAttribute(lstm_tc_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm16);
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, lstm_tc_fwd_kernel<16>, NW * 32, sm16) != cudaSuccess || nblk < 2) {
-                (void)cudaGetLastError();
-                split = 0;
-            }
-        }
-    }
-    const int nbt = split ? 16 : 32;
-    size_t smem = (size_t)nbt * (H + PAD) * 2 + sizeof(float) * NW * (nbt / 8) * 8 * 32 + nbt * UPC * 2 + sizeof(float) * 4 * NW * 32;
-    { const char* e = getenv("EDGEDICT_LSTM_PADSMEM"); if (e) smem += (size_t)atoi(e) * 1024; }   // placement experiments
-    if (split) EB_CUDA(cudaFuncSetAttribute(lstm_tc_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    else EB_CUDA(cudaFuncSetAttribute(lstm_tc_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = (size_t)NBT * (H + PAD) * 2 + sizeof(float) * NW * (NBT / 8) * 8 * 32 + NBT * UPC * 2 +
+                        sizeof(float) * 4 * NW * 32;
+    EB_CUDA(cudaFuncSetAttribute(lstm_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int b0 = 0; b0 < B; b0 += NB) {
         const int nb = (B - b0 < NB) ? (B - b0) : NB;
         FwdP p;
@@ -643,12 +597,9 @@ EB_API int eb_lstm_tc_fwd(const float* xg, const void* whh16, const float* h0, c
         p.bar = reinterpret_cast<unsigned*>(scratch);
         p.hx = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(scratch) + TC_HDR);
         p.B = nb; p.T = T; p.H = H;
-        { const char* e = getenv("EDGEDICT_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
         EB_CUDA(cudaMemsetAsync(scratch, 0, TC_HDR + sizeof(__nv_bfloat16) * (size_t)2 * NB * H, st));
         void* args[] = {&p};
-        const int ntiles = (nb + nbt - 1) / nbt;
-        if (split) EB_CUDA(cudaLaunchCooperativeKernel((void*)lstm_tc_fwd_kernel<16>, dim3(H / UPC, ntiles), dim3(NW * 32), args, smem, st));
-        else EB_CUDA(cudaLaunchCooperativeKernel((void*)lstm_tc_fwd_kernel<32>, dim3(H / UPC, ntiles), dim3(NW * 32), args, smem, st));
+        EB_CUDA(cudaLaunchCooperativeKernel((void*)lstm_tc_fwd_kernel, dim3(H / UPC), dim3(NW * 32), args, smem, st));
     }
     return EB_OK;
 }
