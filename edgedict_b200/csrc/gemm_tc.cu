@@ -269,7 +269,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             const uint32_t acc = (uint32_t)(it & 1), acc_phase = (uint32_t)((it >> 1) & 1);
             const long m0 = mb * BM;
             const int n0 = nb * BN;
-            const bool full = vec_ok && (m0 + BM <= M) && (n0 + BN <= N);
+            const bool full_m = vec_ok && (m0 + BM <= M);
             if (LSE && nb == 0) {                                 // new row block: reset, decode (b,t,u) of my row
                 rm = -INFINITY; rs = 0.f; xb = 0.f; xl = 0.f; lab = -1; cell_ok = false;
                 const long cell = m0 + q * 32 + lane;
@@ -286,6 +286,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             tc_fence_after();
 #pragma unroll 1
             for (int c = (EPW_ == 8 ? chalf : 0); c < BN / 32; c += (EPW_ == 8 ? 2 : 1)) {
+                // a wide tile may hang over the last columns (N % 256 == 128): chunks past N are skipped, chunks
+                // inside keep the vector path
+                if (!LSE && n0 + c * 32 >= N) break;
+                const bool full = full_m && (n0 + c * 32 + 32 <= N);
                 uint32_t r[32];
                 tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c * 32, r);
                 if (empty_split) {
@@ -681,8 +685,12 @@ static int gemm_dispatch(const void* A, int a_mn_major, const void* B, int b_mn_
     if (force_bn < 0) { const char* e = getenv("EDGEDICT_GEMM_BN"); force_bn = e ? atoi(e) : 0; }
     const long wide_tiles = ((M + BM - 1) / BM) * (N / 256);
     bool wide = (N % 256 == 0) && (wide_tiles >= eb_num_sms() || (!c_bf16 && (K + BK - 1) / BK >= 64 && wide_tiles * 4 >= eb_num_sms()));
+    // N = 256 k + 128 with many row blocks (the joint's d-hidden GEMM, N = 640): the 128-wide tiles are bound by
+    // L2 -> SM operand traffic (32 KB per 128x128x64 block); wide tiles with a half-empty last column tile move
+    // 20 % fewer bytes for 20 % more (idle anyway) MMA issue
+    if (!wide && N % 256 == 128 && N >= 512 && (M + BM - 1) / BM >= 4L * eb_num_sms() && accumulate == 0) wide = true;
     if (force_bn == 128) wide = false;
-    if (force_bn == 256 && N % 256 == 0) wide = true;
+    if (force_bn == 256 && N % 128 == 0) wide = true;
     if (low) wide = false;
     CUtensorMap ta, tb;
     bool ok = a_mn_major ? make_map(&ta, A, (uint64_t)M, (uint64_t)K, 64) : make_map(&ta, A, (uint64_t)K, (uint64_t)M, 128);

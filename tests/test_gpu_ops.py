@@ -71,6 +71,26 @@ def test_gemm_bf16_persistent_many_tiles():
     assert rel_err(y.cpu(), ref) < 2e-5
 
 
+def test_gemm_bf16_wide_tiles_overhanging_the_last_columns():
+    """N = 256 k + 128 with many row blocks selects 128x256 tiles whose last column tile hangs over N (the joint's
+    d-hidden GEMM, N = 640): out-of-range columns are never stored, in-range chunks keep the vector path."""
+    from edgedict_b200 import ops
+    M, N, K = 128 * 4 * 148 + 77, 384, 64
+    g = torch.Generator(device="cuda").manual_seed(5)
+    dy = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    w_nt = torch.randn(N, K, device="cuda", generator=g).bfloat16()          # B K-major
+    w_nn = torch.randn(K, N, device="cuda", generator=g).bfloat16()          # B MN-major
+    guard = torch.full((M + 1, N), 7.0, device="cuda").bfloat16()
+    y = ops.gemm_bf16(dy, 0, w_nt, 0, M, N, K, out=guard[:M])
+    ref = dy.float() @ w_nt.float().t()
+    assert rel_err(y.float().cpu(), ref.cpu()) < 1e-2 and (guard[M] == 7.0).all()
+    y2 = ops.gemm_bf16(dy, 0, w_nn, 1, M, N, K)                              # fp32 out
+    assert rel_err(y2.cpu(), (dy.float() @ w_nn.float()).cpu()) < 2e-5
+    hid = torch.tanh(torch.randn(M, N, device="cuda", generator=g)).bfloat16()
+    y3 = ops.gemm_bf16_dtanh(dy, w_nn, True, hid, M, N, K)
+    assert rel_err(y3.float().cpu(), ((dy.float() @ w_nn.float()) * (1 - hid.float() ** 2)).cpu()) < 1e-2
+
+
 @pytest.mark.parametrize("rows,H,res", [(7, 12, False), (33, 240, False), (64, 320, True), (19, 1024, True), (5, 1500, True),
                                         (300, 256, False), (2000, 512, True), (4100, 1024, False), (3, 128, True)])
 def test_layernorm_fwd_bwd(rows, H, res):
