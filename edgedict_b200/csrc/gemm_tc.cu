@@ -684,7 +684,10 @@ static int gemm_dispatch(const void* A, int a_mn_major, const void* B, int b_mn_
     static int force_bn = -1;
     if (force_bn < 0) { const char* e = getenv("EDGEDICT_GEMM_BN"); force_bn = e ? atoi(e) : 0; }
     const long wide_tiles = ((M + BM - 1) / BM) * (N / 256);
-    bool wide = (N % 256 == 0) && (wide_tiles >= eb_num_sms() || (!c_bf16 && (K + BK - 1) / BK >= 64 && wide_tiles * 4 >= eb_num_sms()));
+    // (split-K weight gradients take their parallelism from K: the wide tile only has to exist a few times -- it
+    //  moves 48 KB of operands per 128x256x64 block where two narrow tiles move 64 KB, and these GEMMs sit at the
+    //  L2 -> SM limit, ~12-14 TB/s by l1tex__m_xbar2l1tex_read_bytes)
+    bool wide = (N % 256 == 0) && (wide_tiles >= eb_num_sms() || (!c_bf16 && (K + BK - 1) / BK >= 64 && wide_tiles >= 8));
     // N = 256 k + 128 with many row blocks (the joint's d-hidden GEMM, N = 640): the 128-wide tiles are bound by
     // L2 -> SM operand traffic (32 KB per 128x128x64 block); wide tiles with a half-empty last column tile move
     // 20 % fewer bytes for 20 % more (idle anyway) MMA issue

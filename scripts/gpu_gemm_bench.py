@@ -8,6 +8,7 @@ shapes = [
     ("joint logits  nt fp32-out", 0, 0, 2064000, 1024, 640, False),
     ("joint dhidden nn bf16-out", 0, 1, 2064000, 640, 1024, True),
     ("joint dW2     tn split-K ", 1, 1, 1024, 640, 2064000, False),
+    ("joint dW2^T   tn split-K ", 1, 1, 640, 1024, 2064000, False),
     ("lstm xg       nt fp32-out", 0, 0, 32000, 4096, 1024, False),
     ("lstm dx       nn fp32-out", 0, 1, 32000, 1024, 4096, False),
     ("lstm dW       tn         ", 1, 1, 4096, 1024, 32000, False),

@@ -7,7 +7,8 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size",
         "launch__block_size", "sm__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
-        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed.sum.per_cycle_active"]
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed.sum.per_cycle_active",
+        "l1tex__m_xbar2l1tex_read_bytes.sum"]
 for rep in sorted(glob.glob("gpurun_out/*.ncu-rep")):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
