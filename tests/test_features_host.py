@@ -30,3 +30,31 @@ def test_front_end_has_no_cpu_path():
         m(torch.randn(1, 4000))
     d = Downsample(3)(torch.arange(2 * 5 * 7, dtype=torch.float32).reshape(2, 5, 7))   # pure reshape: device agnostic
     assert np.array_equal(d.numpy(), F.downsample(np.arange(70, dtype=np.float32).reshape(2, 5, 7), 3))
+
+
+def test_wavefront_plan_and_chunk_major_buffers():
+    """Host logic of the layer-wavefront schedule (functional.wavefront_plan / _Chunks): chunk boundaries never
+    split a TimeReduction pair, lengths add up on every layer, scatter/gather are inverse permutations."""
+    from edgedict_b200 import functional as Fn
+    for T, red in [(1000, [0, 1, 0, 0, 0, 0]), (999, [0, 1, 0]), (37, [0, 1]), (133, [1, 0, 1, 0]), (64, [0, 0])]:
+        plan = Fn.wavefront_plan(T, [bool(r) for r in red], max_chunks=4)
+        if plan is None:
+            assert T < 2 * 16 * (1 << sum(red)) or T <= 16 * (1 << sum(red))
+            continue
+        assert len(plan) == len(red) + 1 and sum(plan[0]) == T and 2 <= len(plan[0]) <= 4 + 1
+        gran = 1 << sum(red)
+        assert all(n % gran == 0 for n in plan[0][:-1])                   # only the last chunk may be ragged
+        Tl = T
+        for l, r in enumerate(red):
+            assert sum(plan[l]) == Tl
+            Tl = (Tl + 1) // 2 if r else Tl
+            assert plan[l + 1] == ([(n + 1) // 2 for n in plan[l]] if r else plan[l])
+        assert sum(plan[-1]) == Tl                                         # == the unchunked output length
+    assert Fn.wavefront_plan(1000, [False, True], max_chunks=0) is None    # schedule disabled
+    assert Fn.wavefront_plan(20, [False, True]) is None                    # too short to cut
+    ck = Fn._Chunks(3, [4, 4, 2])
+    x = torch.arange(3 * 10 * 5, dtype=torch.float32).reshape(3, 10, 5)
+    flat = ck.scatter(x)
+    assert flat.shape == (30, 5) and torch.equal(ck.blk(flat, 1), x[:, 4:8]) and torch.equal(ck.gather(flat), x)
+    v = ck.new(0, torch.float32, "cpu")
+    assert v.shape == (30,) and ck.blk(v, 2).shape == (6,)
