@@ -285,7 +285,15 @@ struct BwdP {
     int B, T, H;
 };
 
-template <int CS, bool CLUSTER>
+// REMAP selects the phase-A thread -> (unit, batch row) map:
+//   false (default, every measurement of round 1): unit = warp, row = lane.  A warp-wide load of a saved gate then
+//          touches 32 different 32-byte sectors (one per batch row) for 4 useful bytes each, and the 8 warps of the
+//          CTA re-touch the same sectors: ~1800 sector requests per CTA and step, as much L2 -> SM traffic as the
+//          exchange pull itself, issued right before it;
+//   true  (EDGEDICT_LSTM_BWD_REMAP=1; same arithmetic, NOT yet measured -- the round's GPU budget was spent when
+//          the access pattern was understood): unit = lane / 4, row = 4 * warp + lane % 4, the forward kernel's
+//          map: 8 consecutive units of a row = one sector, 4 sectors per load, ~130 requests per CTA and step.
+template <int CS, bool CLUSTER, bool REMAP = false>
 __global__ void __launch_bounds__(NW * 32, 1) lstm_tc_bwd_kernel(BwdP p) {
     constexpr int MT = CS / 2;                               // m16 tiles: 8*CS units
     constexpr int JS = 8 * CS;                               // units per group
@@ -334,9 +342,10 @@ __global__ void __launch_bounds__(NW * 32, 1) lstm_tc_bwd_kernel(BwdP p) {
             afr[mt][ks][3] = ok ? wpair(u + 8, k + 8) : 0u;
         }
 
-    // phase-A ownership: unit = js*JS + rs*8 + w, batch = lane
-    const int j = js * JS + rs * UPC + w;
-    const int bb = l;
+    // phase-A ownership (see REMAP above): unit = js*JS + rs*8 + uu, batch row = bb
+    const int uu = REMAP ? (l >> 2) : w;
+    const int bb = REMAP ? (w * 4 + (l & 3)) : l;
+    const int j = js * JS + rs * UPC + uu;
     const bool own = bb < B;
     float dh = (own && p.dhT) ? p.dhT[(long)bb * H + j] : 0.f;
     float dc = (own && p.dcT) ? p.dcT[(long)bb * H + j] : 0.f;
@@ -382,10 +391,10 @@ __global__ void __launch_bounds__(NW * 32, 1) lstm_tc_bwd_kernel(BwdP p) {
             pk.y = *reinterpret_cast<uint32_t*>(&hi);
             *reinterpret_cast<uint2*>(gcur + (size_t)bb * H4 + (size_t)j * 4) = pk;
             // gate-major staging for dG_t (weight-gradient GEMMs), stored after the barrier arrival
-            sg[(bb * 4 + 0) * UPC + w] = __low2bfloat16(lo);
-            sg[(bb * 4 + 1) * UPC + w] = __high2bfloat16(lo);
-            sg[(bb * 4 + 2) * UPC + w] = __low2bfloat16(hi);
-            sg[(bb * 4 + 3) * UPC + w] = __high2bfloat16(hi);
+            sg[(bb * 4 + 0) * UPC + uu] = __low2bfloat16(lo);
+            sg[(bb * 4 + 1) * UPC + uu] = __high2bfloat16(lo);
+            sg[(bb * 4 + 2) * UPC + uu] = __low2bfloat16(hi);
+            sg[(bb * 4 + 3) * UPC + uu] = __high2bfloat16(hi);
         }
         __syncthreads();
         ++epoch;
@@ -450,7 +459,7 @@ __global__ void __launch_bounds__(NW * 32, 1) lstm_tc_bwd_kernel(BwdP p) {
 #pragma unroll
             for (int c = 0; c < CS; ++c) {
                 const float* rp = cluster.map_shared_rank(part, c);
-                s += rp[((t & 1) * JS + rs * UPC + w) * NB + l];
+                s += rp[((t & 1) * JS + rs * UPC + uu) * NB + bb];
             }
             dh = s;                                          // dh_rec for (unit j, batch l) at step t-1
             // `part` is double buffered by step parity: a buffer is rewritten two steps later, i.e.
@@ -466,7 +475,7 @@ __global__ void __launch_bounds__(NW * 32, 1) lstm_tc_bwd_kernel(BwdP p) {
             float s = 0.f;
 #pragma unroll
             for (int c = 0; c < CS; ++c)
-                s += __ldcg(p.pglob + ((((size_t)(t & 1) * gridDim.x / CS + js) * CS + c) * JS + rs * UPC + w) * NB + l);
+                s += __ldcg(p.pglob + ((((size_t)(t & 1) * gridDim.x / CS + js) * CS + c) * JS + rs * UPC + uu) * NB + bb);
             dh = s;
         }
     }
@@ -484,6 +493,12 @@ template <int CS>
 size_t bwd_smem(int H) {
     return (size_t)NB * (4 * H / CS + PAD) * 2 + sizeof(float) * (NW * (CS / 2) * 16 * 32 + 2 * 8 * CS * NB) + NB * 4 * UPC * 2 +
            sizeof(float) * 4 * NW * 32;
+}
+
+inline bool bwd_remap() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("EDGEDICT_LSTM_BWD_REMAP"); v = (e && atoi(e)) ? 1 : 0; }
+    return v == 1;
 }
 
 template <int CS>
@@ -510,7 +525,7 @@ int max_clusters(int H) {
 
 template <int CS>
 bool launch_cluster(const BwdP& p, int H, cudaStream_t st) {
-    auto kern = lstm_tc_bwd_kernel<CS, true>;
+    auto kern = bwd_remap() ? lstm_tc_bwd_kernel<CS, true, true> : lstm_tc_bwd_kernel<CS, true, false>;
     const size_t smem = bwd_smem<CS>(H);
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
         (void)cudaGetLastError();
@@ -638,7 +653,7 @@ EB_API int eb_lstm_tc_bwd(const float* dy, const float* gates, const float* cseq
         else if (cs == 2) launched = launch_cluster<2>(p, H, st);
         if (!launched) {
             // software reduce-scatter through L2: plain cooperative grid, always co-resident
-            auto kern = lstm_tc_bwd_kernel<4, false>;
+            auto kern = bwd_remap() ? lstm_tc_bwd_kernel<4, false, true> : lstm_tc_bwd_kernel<4, false, false>;
             const size_t smem = bwd_smem<4>(H);
             EB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             void* args[] = {&p};
