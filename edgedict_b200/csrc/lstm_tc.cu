@@ -292,7 +292,7 @@ struct BwdP {
 //          exchange pull itself, issued right before it;
 //   true  (EDGEDICT_LSTM_BWD_REMAP=1; same arithmetic, NOT yet measured -- the round's GPU budget was spent when
 //          the access pattern was understood): unit = lane / 4, row = 4 * warp + lane % 4, the forward kernel's
-//          map: 8 consecutive units of a row = one sector, 4 sectors per load, ~130 requests per CTA and step.
+//          map: 8 consecutive units of a row = one sector, 4 sectors per load, ~220 requests per CTA and step.
 template <int CS, bool CLUSTER, bool REMAP = false>
 __global__ void __launch_bounds__(NW * 32, 1) lstm_tc_bwd_kernel(BwdP p) {
     constexpr int MT = CS / 2;                               // m16 tiles: 8*CS units
