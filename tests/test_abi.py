@@ -101,3 +101,30 @@ def test_model_refuses_cpu_tensors():
     enc = Encoder(8, 16, 1, 0, 8)
     with pytest.raises(RuntimeError, match="CUDA"):
         enc(torch.zeros(1, 4, 8))
+
+
+def test_entry_points_reject_bad_arguments_before_touching_the_device(built):
+    """Error behaviour of the C ABI (status 2 = invalid value, as rnntStatus_t RNNT_STATUS_INVALID_VALUE): argument
+    checks run before any CUDA call, so they are testable without a GPU."""
+    from edgedict_b200._lib import lib
+    L = lib()
+    p = 1 << 20                                               # a plausible, aligned, never dereferenced address
+    assert L.eb_gemm_bf16(None, 0, p, 0, p, 0, None, 0, 8, 8, 8, None) == 2
+    assert L.eb_gemm_bf16(p, 0, p, 0, p, 0, None, 0, 8, 8, 12, None) == 2            # K-major rows must be 16-byte multiples
+    assert L.eb_gemm_bf16(p + 2, 0, p, 0, p, 0, None, 0, 8, 8, 8, None) == 2         # misaligned operand
+    assert L.eb_gemm_bf16_ex(p, 1, p, 0, p, 0, None, 0, 8, 8, 8, 1, None) == 2       # co-resident config: K-major only
+    assert L.eb_gemm_bf16_dtanh(p, 0, p, 1, p, None, 8, 8, 8, None) == 2             # needs the hidden activations
+    assert L.eb_gemm_bf16_dtanh(p, 0, p, 1, p, p, 8, 6, 8, None) == 2                # N % 4
+    assert L.eb_joint_dpre_reduce(None, p, p, 1, 1, 1, 8, None) == 2
+    assert L.eb_joint_dpre_reduce(p, p, p, 1, 1, 1, 12, None) == 2                   # J % 8
+    assert L.eb_joint_logits_lse(p, p, None, p, p, p, p, p, p, p, 1, 1, 1, 8, 12, 0, None) == 2   # J % 8
+    assert L.eb_joint_logits_lse(p, p, None, p, p, p, p, p, p, p, 1, 1, 1, 8, 8, 9, None) == 2    # blank >= V
+    assert L.eb_fe_preemph_pad(None, p, 1, 100, 400, 8, 0.97, 1, None) == 2
+    assert L.eb_fe_preemph_pad(p, p, 1, 100, 100, 8, 0.97, 1, None) == 2             # Lp < L + 2*pad
+    assert L.eb_fe_power(p, None, 4, 4, None) == 2
+    assert L.eb_fe_log_stack(p, p, 1, 3, 5, 5, 8, 1, 5, 1, None) == 2                # rows_per_utt < n_frames
+    assert L.eb_lstm_tc_supported(32, 1024) == 1 and L.eb_lstm_tc_supported(32, 1000) == 0
+    assert L.eb_lstm_tc_supported(32, 2048) == 0 and L.eb_lstm_tc_scratch_bytes(32, 1000) == 0
+    assert L.eb_lstm_tc_fwd(None, p, None, None, p, p, p, p, None, None, p, 4, 3, 64, None) == 2
+    assert L.eb_lstm_tc_fwd(p, p, None, None, p, p, p, p, None, None, p, 4, 0, 64, None) == 2     # T <= 0
+    assert L.eb_lstm_tc_bwd(p, p, p, None, p, None, None, p, p, p, p, 4, 3, 96, None) == 2        # H % 64
