@@ -8,10 +8,16 @@
   torchrun --nproc-per-node N bench.py --gpus N ...        (one rank per GPU, NCCL)
 
 "ours": the B200 engine in bf16 mode (tcgen05 GEMMs, fp32 accumulate / fp32 recurrent state),
-weak scaling (B=32 per GPU), one all-reduce of the flat gradient bucket per step.
+weak scaling (B=32 per GPU), one all-reduce of the flat gradient bucket per step; the line also carries
+`strong_scaling` (BASELINE configs[2]: global B=256 as 8/N accumulation micro-steps of 32 per GPU, one all-reduce
+per optimizer step -- the reference's sub_batch mechanism, cli/baseline.py:214-237) and `parity_probe` (loss of the
+bf16 bench mode against the fp32 parity mode of the same weights).  `--scaling strong` makes the strong-scaling
+figure the headline instead.
 "reference": the reference's own CPU path restated in oracle/model_torch.py (torch-CPU fp32,
-nn.LSTM's ATen kernel) + the reference's compiled warp-transducer CPU library (oracle/_ref) --
-a bounded sample of the same workload on the host cores.
+nn.LSTM's ATen kernel) + the reference's compiled warp-transducer CPU library (oracle/_ref) on the SAME config:
+the B=32 step is executed the way the reference itself runs a large batch on a small device, as accumulation
+sub-batches of the same utterance shape (T=1000, U=128); each timed "step" is one sub-batch (a bounded sample:
+1/16 of the optimizer step), the optimizer update is applied every 16th sub-batch inside the timed region.
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -30,6 +36,7 @@ E6D2 = dict(vocab_embed_size=64, vocab_size=1024, input_size=240, enc_hidden_siz
             enc_dropout=0.0, enc_proj_size=640, dec_hidden_size=256, dec_layers=2, dec_dropout=0.0,
             dec_proj_size=256, joint_size=640)
 B, T, U, V = 32, 1000, 128, 1024
+GLOBAL_B = 256              # BASELINE configs[2]
 
 
 def peaks():
@@ -101,12 +108,21 @@ def run_ours(args):
     # pinned host copies for the end-to-end leg
     hx, hy = xs.cpu().pin_memory(), ys.cpu().pin_memory()
 
-    def step(x, y):
+    strong = args.scaling == "strong"
+    micro = max(1, GLOBAL_B // (B * world))           # configs[2]: B=256 global -> 8/N micro-steps of 32 per GPU
+    if strong:
+        assert B * world * micro == GLOBAL_B, "strong scaling needs N in {1, 2, 4, 8}"
+
+    def step(x, y, n_micro=None):
+        """One optimizer step: n_micro accumulation micro-steps (gradients add up in the flat bucket), ONE all-reduce,
+        one fused Adam launch with the 1/n_micro scale folded in."""
+        n_micro = (micro if strong else 1) if n_micro is None else n_micro
         opt.zero_grad()
-        loss = model(x, y, xlen, ylen)
-        loss.backward()
+        for _ in range(n_micro):
+            loss = model(x, y, xlen, ylen)
+            loss.backward()
         ed.allreduce_bucket(opt.flat_grads, world)
-        opt.step()
+        opt.step(grad_scale=1.0 / n_micro)
         return loss
 
     def barrier():
@@ -119,6 +135,8 @@ def run_ours(args):
         loss = step(xs, ys)
     barrier()
     first_loss = float(loss.detach())
+    probe = parity_probe(model, dev) if rank == 0 else None
+    barrier()
 
     # ---- leg 1: inputs resident in HBM, per-kernel events on --------------------------------------
     sampler = ClockSampler(local)
@@ -192,10 +210,22 @@ def run_ours(args):
     last_loss = host_losses[-1]
     assert len(host_losses) == args.steps
 
+    # ---- leg 3: BASELINE configs[2] strong scaling (global B=256), two optimizer steps after one warm-up
+    strong_ms = None
+    if not strong and B * world * micro == GLOBAL_B:
+        step(xs, ys, micro)
+        barrier()
+        e0.record()
+        for _ in range(2):
+            step(xs, ys, micro)
+        e1.record()
+        barrier()
+        strong_ms = ed.max_over_ranks(e0.elapsed_time(e1), dev) / 2
+
     if rank != 0:
         return None
     pk = peaks()
-    audio = world * B * T * FRAME_SEC
+    audio = world * B * T * FRAME_SEC * (micro if strong else 1)
     kern = {}
     for name, d in prof.items():
         ms = d["ms"] / args.steps
@@ -245,32 +275,53 @@ def run_ours(args):
                       what=note)
     out = dict(metric="audio-sec/sec E6D2 B=32 T=1000 U=128 V=1024 training step", value=round(audio / ms_dev * 1e3, 1),
                unit="audio-sec/sec", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
-               ms_per_step=round(ms_dev, 3), higher_is_better=True, scaling="weak", vs_baseline=None,
+               ms_per_step=round(ms_dev, 3), higher_is_better=True, scaling="strong" if strong else "weak", vs_baseline=None,
                dtype="bf16" if args.precision == "bf16" else "f32", data="synthetic",
                config=dict(workload="E6D2 (6x1024 LSTM enc / 2x256 pred / joint 640 / V=1024) fwd+loss+bwd+Adam, "
                                     "B=32/GPU T=1000 U=128 (configs[1]); frame=37.5 ms",
-                           global_batch=B * world, seq_len=T, parallelism="dp%d" % world,
+                           global_batch=B * world * (micro if strong else 1), seq_len=T, parallelism="dp%d" % world,
+                           micro_steps_per_optimizer_step=micro if strong else 1,
                            l2="inputs >> L2: 4.2 GB of bf16 logits (8.45 GB with EDGEDICT_FUSE_LSE=0) streamed per step"),
                e2e=dict(value=round(audio / ms_e2e * 1e3, 1), unit="audio-sec/sec",
                         h2d_bytes_per_step=hx.numel() * 4 + hy.numel() * 4, d2h_bytes_per_step=4,
                         ms_per_step=round(ms_e2e, 3), host_ms_per_iteration=step_wall),
                gpu_launches=launches, clocks=clocks, roofline=roof, joint_loss_hbm=joint_loss, kernels=kern,
-               loss_first=round(first_loss, 4), loss_last=round(last_loss, 4))
+               loss_first=round(first_loss, 4), loss_last=round(last_loss, 4), parity_probe=probe)
+    if strong_ms is not None:
+        out["strong_scaling"] = dict(global_batch=GLOBAL_B, micro_steps=micro, ms_per_optimizer_step=round(strong_ms, 3),
+                                     value=round(GLOBAL_B * T * FRAME_SEC / strong_ms * 1e3, 1), unit="audio-sec/sec",
+                                     what="BASELINE configs[2]: 8/N accumulation micro-steps of B=32 per GPU, one "
+                                          "all-reduce + one Adam launch per optimizer step")
     return out
 
 
-def cpu_sample_shape(total_steps):
-    """Bounded sample of the E6D2 B=32 T=1000 U=128 step (same model, same T:U ratio), sized so that
-    warm-up + timed steps stay within a couple of minutes on the host cores."""
-    if total_steps <= 2:
-        return 2, 500, 64
-    if total_steps <= 10:
-        return 1, 250, 32
-    return 1, 128, 16
+def parity_probe(model, dev):
+    """Loss of the bf16 bench mode against the fp32 parity mode (same weights, same inputs) on a probe batch of the
+    benchmark's hidden sizes: the figure tests/test_gpu_parity_bf16.py asserts against the CPU oracle."""
+    import torch
+    g = torch.Generator(device=dev).manual_seed(123)
+    xs = torch.randn(4, 200, 240, device=dev, generator=g)
+    ys = torch.randint(4, V, (4, 32), device=dev, dtype=torch.int32, generator=g)
+    xlen = torch.tensor([200, 200, 171, 150], dtype=torch.int32)
+    ylen = torch.tensor([32, 25, 32, 17], dtype=torch.int32)
+    with torch.no_grad():
+        l16 = float(model(xs, ys, xlen, ylen))
+        model.set_precision("fp32")
+        l32 = float(model(xs, ys, xlen, ylen))
+        model.set_precision("bf16")
+    return dict(shape="E6D2 B=4 T=200 U=32 ragged", loss_bf16=round(l16, 5), loss_fp32=round(l32, 5),
+                rel_err=abs(l16 - l32) / abs(l32), bar=1e-3)
 
 
-def run_reference(steps, warmup, timed_only=False):
-    """The reference's CPU path (oracle port of rnnt/models.py + compiled warp-transducer CPU loss)."""
+REF_SUB_B = 2               # utterances per accumulation sub-batch of the CPU arm (same T, U as the GPU arm)
+
+
+def run_reference(steps, warmup, sub_b=REF_SUB_B):
+    """The reference's CPU path (oracle port of rnnt/models.py + compiled warp-transducer CPU loss) on the bench
+    config: B=32 T=1000 U=128 executed as 32/sub_b accumulation sub-batches of identical shape, the reference's own
+    mechanism for batches that do not fit a device (cli/baseline.py:214-237).  One timed "step" = one sub-batch
+    (forward + loss + backward into the accumulated gradients); the Adam update runs once every 32/sub_b
+    sub-batches, inside the timed region.  audio-sec/sec = sub_b * T * 37.5 ms / seconds per sub-batch."""
     import torch
     from oracle import loss as ol
     from oracle import model_torch as mt
@@ -285,18 +336,22 @@ def run_reference(steps, warmup, timed_only=False):
     shell = Transducer(**E6D2)
     sd = {k: v.detach().clone().requires_grad_(True) for k, v in shell.state_dict().items()}
     optim = torch.optim.Adam(list(sd.values()), lr=5e-4)
-    Bs, Ts, Us = cpu_sample_shape(steps + warmup)
+    n_sub = B // sub_b
     torch.manual_seed(10)
-    xs = torch.randn(Bs, Ts, 240)
-    ys = torch.randint(4, V, (Bs, Us), dtype=torch.int32)
-    xlen, ylen = torch.full((Bs,), Ts, dtype=torch.int32), torch.full((Bs,), Us, dtype=torch.int32)
+    xs = torch.randn(sub_b, T, 240)
+    ys = torch.randint(4, V, (sub_b, U), dtype=torch.int32)
+    xlen, ylen = torch.full((sub_b,), T, dtype=torch.int32), torch.full((sub_b,), U, dtype=torch.int32)
+    done = [0]
 
     def one():
-        optim.zero_grad()
-        loss = mt.transducer_loss(sd, xs, ys, xlen, ylen, fast=True, use_ref=True)
+        if done[0] % n_sub == 0:
+            optim.zero_grad()
+        loss = mt.transducer_loss(sd, xs, ys, xlen, ylen, fast=True, use_ref=True) / n_sub
         loss.backward()
-        optim.step()
-        return float(loss.detach())
+        done[0] += 1
+        if done[0] % n_sub == 0:
+            optim.step()
+        return float(loss.detach()) * n_sub
 
     for _ in range(warmup):
         one()
@@ -304,9 +359,10 @@ def run_reference(steps, warmup, timed_only=False):
     for _ in range(steps):
         one()
     dt = (time.perf_counter() - t0) / steps
-    val = Bs * Ts * FRAME_SEC / dt
+    val = sub_b * T * FRAME_SEC / dt
     kind = "reference" if ol.have_ref() else "port"
-    sample = "B=%d T=%d U=%d V=1024 E6D2 fwd+loss+bwd+Adam fp32, %d step(s)" % (Bs, Ts, Us, steps)
+    sample = ("E6D2 B=32 T=1000 U=128 V=1024 fwd+loss+bwd+Adam fp32 as %d accumulation sub-batches of B=%d T=%d U=%d; "
+              "%d sub-batch(es) timed (%.1f s each), optimizer step every %d" % (n_sub, sub_b, T, U, steps, dt, n_sub))
     return dict(value=round(val, 3), unit="audio-sec/sec", cores=cores,
                 kind=kind + " (warp-transducer CPU lib compiled from the reference; model = torch-CPU port "
                             "calling the same ATen LSTM kernel as nn.LSTM)", sample=sample), dt
@@ -320,17 +376,25 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     if args.impl == "reference":
         if rank != 0:
             return
-        cb, dt = run_reference(args.steps, args.warmup)
+        # a sub-batch of the full-size utterances takes several seconds on the host: keep the whole run within minutes
+        steps, warmup = min(args.steps, 8), min(args.warmup, 1)
+        cb, dt = run_reference(steps, warmup)
         print(json.dumps(dict(impl="reference", metric="audio-sec/sec E6D2 B=32 T=1000 U=128 V=1024 training step",
-                              value=cb["value"], unit="audio-sec/sec", n_gpus=args.gpus, steps=args.steps,
-                              warmup=args.warmup, ms_per_step=round(dt * 1e3, 1), higher_is_better=True,
+                              value=cb["value"], unit="audio-sec/sec", n_gpus=args.gpus, steps=steps,
+                              warmup=warmup, requested_steps=args.steps, requested_warmup=args.warmup,
+                              ms_per_step=round(dt * 1e3 * (B // REF_SUB_B), 1), higher_is_better=True,
                               scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-                              config=dict(workload="E6D2 training step on host cores, bounded sample: " + cb["sample"]),
+                              config=dict(workload="E6D2 (6x1024 LSTM enc / 2x256 pred / joint 640 / V=1024) fwd+loss+bwd+Adam, "
+                                                   "B=32/GPU T=1000 U=128 (configs[1]); frame=37.5 ms",
+                                          global_batch=B, seq_len=T, parallelism="host cores",
+                                          sub_batches_timed=steps, sub_batches_warmup=warmup,
+                                          how=cb["sample"]),
                               cpu_baseline=cb, gpu_launches=0,
                               e2e=dict(value=cb["value"], unit="audio-sec/sec", h2d_bytes_per_step=0,
                                        d2h_bytes_per_step=0))))
@@ -343,7 +407,7 @@ def main():
     if out is None:
         return
     if args.gpus == 1 and not args.no_cpu_baseline:
-        cb, _ = run_reference(1, 1)          # 1 warm-up + 1 timed step of the bounded sample
+        cb, _ = run_reference(2, 1)          # 1 warm-up + 2 timed sub-batches of the full-size utterances
         out["cpu_baseline"] = cb
     print(json.dumps(out))
 

@@ -32,6 +32,15 @@ SIGNATURES = {
     "eb_lstm_tc_max_clusters": (I, [I, I]),
     "eb_lstm_tc_fwd": (I, [P, P, P, P, P, P, P, P, P, P, P, I, I, I, P]),
     "eb_lstm_tc_bwd": (I, [P, P, P, P, P, P, P, P, P, P, P, I, I, I, P]),
+    "eb_lstm_c4_supported": (I, [I, I]),
+    "eb_lstm_c4_bwd_cluster": (I, [I]),
+    "eb_lstm_c4_max_clusters": (I, [I, I]),
+    "eb_lstm_c4_set_trace": (I, [P, I]),
+    "eb_lstm_c4_scratch_bytes": (Z, [I, I]),
+    "eb_lstm_c4_gsave_bytes": (Z, [I, I, I]),
+    "eb_lstm_c4_csave_bytes": (Z, [I, I, I]),
+    "eb_lstm_c4_fwd": (I, [P, P, P, P, P, P, P, P, P, P, P, I, I, I, P]),
+    "eb_lstm_c4_bwd": (I, [P, P, P, P, P, P, P, P, P, P, P, I, I, I, P]),
     "eb_layernorm_fwd": (I, [P, P, P, P, P, P, P, P, L, I, F, P]),
     "eb_layernorm_bwd": (I, [P, P, P, P, P, P, P, P, P, L, I, P]),
     "eb_time_reduce_fwd": (I, [P, P, P, I, I, I, P]),
@@ -46,6 +55,7 @@ SIGNATURES = {
     "eb_cast_bf16": (I, [P, P, L, P]),
     "eb_transpose_to_bf16": (I, [P, I, P, L, L, P]),
     "eb_adam_step": (I, [P, P, P, P, L, F, F, F, F, F, I, F, P]),
+    "eb_adam_step_ex": (I, [P, P, P, P, L, F, F, F, F, F, I, F, P, F, I, P]),
     "eb_sumsq": (I, [P, L, P, P]),
     "eb_fe_preemph_pad": (I, [P, P, I, I, L, I, F, I, P]),
     "eb_fe_power": (I, [P, P, L, I, P]),

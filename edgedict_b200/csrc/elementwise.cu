@@ -531,6 +531,40 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     }
 }
 
+// Adam / AdamW over the flat bucket with the gradient clip and the loss-scale handling folded in:
+//   gscale      = 1 / loss_scale (and 1 / accumulation steps): every gradient is multiplied by it;
+//   sumsq       = device scalar holding sum(g^2) of the UNSCALED bucket (eb_sumsq), or null: no clip, no overflow test;
+//   max_norm>0  : torch.nn.utils.clip_grad_norm_ semantics, coef = max_norm / (norm + 1e-6) applied when < 1
+//                 (cli/baseline.py:239-245);
+//   a non-finite norm (overflow under loss scaling) skips the update entirely, as apex's scaler does;
+//   adamw       : the reference's own AdamW (modules/optimizer.py:283-290): p -= lr*sqrt(bc2)/bc1 * (wd*p + m/(sqrt(v)+eps));
+//                 else torch.optim.Adam with L2 weight decay added to the gradient.
+__global__ void adam_ex_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                               float* __restrict__ v, long n, float lr, float b1, float b2, float eps, float wd,
+                               float bc1, float bc2, float gscale, const float* __restrict__ sumsq, float max_norm,
+                               int adamw) {
+    float coef = gscale;
+    if (sumsq) {
+        const float norm = sqrtf(*sumsq) * fabsf(gscale);
+        if (!isfinite(norm)) return;
+        if (max_norm > 0.f) {
+            const float c = max_norm / (norm + 1e-6f);
+            if (c < 1.f) coef *= c;
+        }
+    }
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        float gi = g[i] * coef;
+        const float pi = p[i];
+        if (!adamw && wd != 0.f) gi += wd * pi;
+        const float mi = b1 * m[i] + (1.f - b1) * gi;
+        const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        if (adamw) p[i] = pi - (lr * sqrtf(bc2) / bc1) * (wd * pi + mi / (sqrtf(vi) + eps));
+        else p[i] = pi - (lr / bc1) * (mi / (sqrtf(vi) / sqrtf(bc2) + eps));
+    }
+}
+
 __global__ void sumsq_kernel(const float* __restrict__ x, long n, float* __restrict__ out) {
     __shared__ float sh[33];
     float acc = 0.f;
@@ -743,6 +777,17 @@ EB_API int eb_adam_step(float* p, const float* g, float* m, float* v, long n, fl
     float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
     adam_kernel<<<ew_grid(n, 256), 256, 0, ST(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps,
                                                          weight_decay, bc1, bc2, grad_scale);
+    EB_CHECK_LAUNCH();
+    return EB_OK;
+}
+
+EB_API int eb_adam_step_ex(float* p, const float* g, float* m, float* v, long n, float lr, float beta1, float beta2,
+                           float eps, float weight_decay, int step, float grad_scale, const float* sumsq,
+                           float max_norm, int adamw, void* stream) {
+    if (!p || !g || !m || !v || n <= 0 || step < 1) return EB_ERR_INVALID;
+    float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
+    adam_ex_kernel<<<ew_grid(n, 256), 256, 0, ST(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2,
+                                                            grad_scale, sumsq, max_norm, adamw);
     EB_CHECK_LAUNCH();
     return EB_OK;
 }

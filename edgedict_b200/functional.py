@@ -120,14 +120,18 @@ class LSTMLayer(torch.autograd.Function):
         c0c = _c(c0) if c0 is not None else None
         need = any(ctx.needs_input_grad)     # (grad mode is off inside Function.forward)
         tc = precision == "bf16" and ops.lstm_tc_supported(B, H)
-        if tc:
+        c4 = precision == "bf16" and ops.lstm_c4_supported(B, H)
+        if c4:
+            # cluster / tcgen05 kernels: saves in their CTA-private layout, y16 IS the h_{t-1}-shifted copy
+            y, y16, hT, cT, gates, cseq = ops.lstm_c4_fwd(xg, ops.cast_bf16(_c(w_hh)), h0c, c0c, need)
+        elif tc:
             y, y16, hT, cT, gates, cseq = ops.lstm_tc_fwd(xg, ops.cast_bf16(_c(w_hh)), h0c, c0c, need)
         else:
             y, hT, cT, gates, cseq = ops.lstm_seq_fwd(xg, _c(w_hh), h0c, c0c, need)
             y16 = None
         if need:
-            ctx.save_for_backward(x2 if x16 is None else x16, h0c, c0c, w_ih, w_hh, y16 if tc else y, gates, cseq)
-            ctx.precision, ctx.dims, ctx.tc = precision, (B, T, I, H), tc
+            ctx.save_for_backward(x2 if x16 is None else x16, h0c, c0c, w_ih, w_hh, y16 if (tc or c4) else y, gates, cseq)
+            ctx.precision, ctx.dims, ctx.tc, ctx.c4 = precision, (B, T, I, H), tc, c4
         return y, hT, cT
 
     @staticmethod
@@ -138,7 +142,14 @@ class LSTMLayer(torch.autograd.Function):
         dy = _c(dy) if dy is not None else torch.zeros(B, T, H, dtype=f32, device=y.device)
         dhT = _c(dhT) if dhT is not None else None
         dcT = _c(dcT) if dcT is not None else None
-        if ctx.tc:
+        if getattr(ctx, "consumed", False):
+            raise RuntimeError("LSTMLayer.backward ran twice on the same graph: the saved gates are overwritten in "
+                               "place by the first pass (retain_graph is not supported by this node)")
+        ctx.consumed = True
+        if ctx.c4:
+            dg16, dh0, dc0 = ops.lstm_c4_bwd(dy, gates, cseq, c0, ops.transpose_to_bf16(_c(w_hh)), dhT, dcT)
+            dg2 = dg16.view(B * T, 4 * H)
+        elif ctx.tc:
             dg16, dh0, dc0 = ops.lstm_tc_bwd(dy, gates, cseq, c0, ops.transpose_to_bf16(_c(w_hh)), dhT, dcT)
             dg2 = dg16.view(B * T, 4 * H)
         else:
@@ -146,14 +157,17 @@ class LSTMLayer(torch.autograd.Function):
             dg2 = dg.view(B * T, 4 * H)
             dg16 = ops.cast_bf16(dg2) if p == "bf16" else None
         dg16 = dg16.view(B * T, 4 * H) if dg16 is not None else None
-        # h_{t-1} for every step: y shifted right by one frame, h0 (or zeros) in front
-        hprev = torch.empty_like(y)
-        hprev[:, 1:] = y[:, :-1]
-        if h0 is not None:
-            hprev[:, 0] = h0
+        if ctx.c4:
+            hp2 = y.view(B * T, H)                           # the kernel already wrote h_{t-1} for every step
         else:
-            hprev[:, 0].zero_()
-        hp2 = hprev.view(B * T, H)
+            # h_{t-1} for every step: y shifted right by one frame, h0 (or zeros) in front
+            hprev = torch.empty_like(y)
+            hprev[:, 1:] = y[:, :-1]
+            if h0 is not None:
+                hprev[:, 0] = h0
+            else:
+                hprev[:, 0].zero_()
+            hp2 = hprev.view(B * T, H)
         dx = ops.mm_nn(dg2, w_ih, p, dy16=dg16).view(B, T, I) if ctx.needs_input_grad[0] else None
         dw_ih = ops.mm_tn(dg2, xs, p, dy16=dg16, x16=xs if p == "bf16" else None)
         dw_hh = ops.mm_tn(dg2, hp2, p, dy16=dg16, x16=hp2 if hp2.dtype == bf16 else None)
@@ -246,6 +260,8 @@ class LSTMStack(torch.autograd.Function):
     args: x [B,T,I] fp32, cfg = (reductions, eps, plan), then per layer w_ih, w_hh, b_ih, b_hh, ln_w, ln_b.
     returns y [B,T',H], h_T [L,B,H], c_T [L,B,H] (final states: not differentiated through)."""
 
+    collect = None      # tests: set to a list to receive every layer's output [B,T_l,H] (parity of the per-layer activations)
+
     @staticmethod
     def forward(ctx, x, cfg, *params):
         reductions, eps, plan = cfg
@@ -255,6 +271,7 @@ class LSTMStack(torch.autograd.Function):
         H = params[1].shape[1]
         C = len(plan[0])
         need = any(ctx.needs_input_grad)
+        c4 = ops.lstm_c4_supported(B, H)
         ck = [_Chunks(B, lens) for lens in plan]
         P = [params[6 * l:6 * l + 6] for l in range(L)]
         wih16 = [ops.cast_bf16(_c(p[0])) for p in P]
@@ -267,9 +284,9 @@ class LSTMStack(torch.autograd.Function):
         for l in range(L):
             k, kn = ck[l], ck[l + 1]
             y[l] = k.new(H, f32, dev)
-            y16[l] = k.new(H, bf16, dev)
-            gates[l] = k.new(4 * H, f32, dev) if need else None
-            cseq[l] = k.new(H, f32, dev) if need else None
+            y16[l] = k.new(H, bf16, dev) if (need or not c4) else None     # c4: holds h_{t-1} (the dW_hh operand)
+            gates[l] = k.new(4 * H, f32, dev) if (need and not c4) else None
+            cseq[l] = k.new(H, f32, dev) if (need and not c4) else None
             mean[l], rstd[l] = k.new(0, f32, dev), k.new(0, f32, dev)
             xs[l + 1] = kn.new(H, f32, dev)
             z[l] = k.new(H, f32, dev) if reductions[l] else xs[l + 1]
@@ -277,6 +294,7 @@ class LSTMStack(torch.autograd.Function):
         hT = torch.empty(L, C, B, H, dtype=f32, device=dev)
         cT = torch.empty(L, C, B, H, dtype=f32, device=dev)
         xgbuf = [torch.empty(B * max(plan[0]), 4 * H, dtype=f32, device=dev) for _ in range(2)]
+        c4saves = [[None] * C for _ in range(L)]               # c4: per (layer, chunk) saves in the kernels' layout
 
         main = torch.cuda.current_stream(dev)
         side = _side_streams(dev)
@@ -296,10 +314,19 @@ class LSTMStack(torch.autograd.Function):
                     xg = xgbuf[l % 2][:B * Tc]
                     ops.gemm_bf16(xin.view(B * Tc, xin.shape[2]), 0, wih16[l], 0, B * Tc, 4 * H, xin.shape[2],
                                   bias=bias[l], out=xg, flags=ops.GEMM_CORESIDENT)
-                    ops.lstm_tc_fwd(xg.view(B, Tc, 4 * H), whh16[l], hT[l, c - 1] if c else None,
-                                    cT[l, c - 1] if c else None, need,
-                                    out=(k.blk(y[l], c), k.blk(y16[l], c), hT[l, c], cT[l, c],
-                                         k.blk(gates[l], c) if need else None, k.blk(cseq[l], c) if need else None))
+                    if c4:
+                        r = ops.lstm_c4_fwd(xg.view(B, Tc, 4 * H), whh16[l], hT[l, c - 1] if c else None,
+                                            cT[l, c - 1] if c else None, need,
+                                            out=(k.blk(y[l], c), k.blk(y16[l], c) if need else None, hT[l, c], cT[l, c]))
+                        if need:
+                            c4saves[l][c] = (r[4], r[5])
+                            r[4].record_stream(main)
+                            r[5].record_stream(main)
+                    else:
+                        ops.lstm_tc_fwd(xg.view(B, Tc, 4 * H), whh16[l], hT[l, c - 1] if c else None,
+                                        cT[l, c - 1] if c else None, need,
+                                        out=(k.blk(y[l], c), k.blk(y16[l], c), hT[l, c], cT[l, c],
+                                             k.blk(gates[l], c) if need else None, k.blk(cseq[l], c) if need else None))
                     res = k.blk(xs[l], c) if l else None
                     nx16 = kn.blk(x16[l + 1], c) if x16[l + 1] is not None else None
                     if reductions[l]:
@@ -313,10 +340,16 @@ class LSTMStack(torch.autograd.Function):
         for s in side:
             main.wait_stream(s)
         out = ck[L].gather(xs[L])
+        if LSTMStack.collect is not None:
+            LSTMStack.collect.extend(ck[l + 1].gather(xs[l + 1]) for l in range(L))
         hT_last, cT_last = hT[:, C - 1].contiguous(), cT[:, C - 1].contiguous()
         if need:
-            ctx.save_for_backward(*params, hT, cT, *x16[:L], *xs[1:L], *y, *y16, *gates, *cseq, *mean, *rstd)
-            ctx.cfg, ctx.dims = cfg, (B, T, I0, H, L, C)
+            if c4:
+                gates = [torch.empty(0, device=dev)] * L
+                cseq = [torch.empty(0, device=dev)] * L
+            flat_saves = [t for row in c4saves for pair in row for t in pair] if c4 else []
+            ctx.save_for_backward(*params, hT, cT, *x16[:L], *xs[1:L], *y, *y16, *gates, *cseq, *mean, *rstd, *flat_saves)
+            ctx.cfg, ctx.dims, ctx.c4 = cfg, (B, T, I0, H, L, C), c4
         ctx.mark_non_differentiable(hT_last, cT_last)
         return out, hT_last, cT_last
 
@@ -331,6 +364,11 @@ class LSTMStack(torch.autograd.Function):
         x16, sv = sv[:L], sv[L:]
         xs, sv = [None] + sv[:L - 1], sv[L - 1:]
         y, y16, gates, cseq, mean, rstd = (sv[i * L:(i + 1) * L] for i in range(6))
+        c4 = ctx.c4
+        flat_saves = sv[6 * L:]
+        if getattr(ctx, "consumed", False):
+            raise RuntimeError("LSTMStack.backward ran twice on the same graph (retain_graph is not supported)")
+        ctx.consumed = True
         P = [params[6 * l:6 * l + 6] for l in range(L)]
         ck = [_Chunks(B, lens) for lens in plan]
         dev = dout.device
@@ -346,17 +384,24 @@ class LSTMStack(torch.autograd.Function):
             dz, dgamma, dbeta = ops.layernorm_bwd(g, y[l], xs[l], P[l][4], mean[l], rstd[l])
             whhT16 = ops.transpose_to_bf16(_c(P[l][1]))
             dg16 = k.new(4 * H, bf16, dev)
-            hprev = k.new(H, bf16, dev)
             dh = dc = None
-            for c in range(C - 1, -1, -1):
-                _, dh, dc = ops.lstm_tc_bwd(k.blk(dz, c), k.blk(gates[l], c), k.blk(cseq[l], c),
-                                            cT[l, c - 1] if c else None, whhT16, dh, dc, out=k.blk(dg16, c))
-                hp, yc = k.blk(hprev, c), k.blk(y16[l], c)
-                hp[:, 1:] = yc[:, :-1]
-                if c:
-                    hp[:, 0] = k.blk(y16[l], c - 1)[:, -1]
-                else:
-                    hp[:, 0].zero_()
+            if c4:
+                hprev = y16[l]                                # written by the forward kernel
+                for c in range(C - 1, -1, -1):
+                    gs, cs = flat_saves[2 * (l * C + c)], flat_saves[2 * (l * C + c) + 1]
+                    _, dh, dc = ops.lstm_c4_bwd(k.blk(dz, c), gs, cs, cT[l, c - 1] if c else None, whhT16, dh, dc,
+                                                out=k.blk(dg16, c))
+            else:
+                hprev = k.new(H, bf16, dev)
+                for c in range(C - 1, -1, -1):
+                    _, dh, dc = ops.lstm_tc_bwd(k.blk(dz, c), k.blk(gates[l], c), k.blk(cseq[l], c),
+                                                cT[l, c - 1] if c else None, whhT16, dh, dc, out=k.blk(dg16, c))
+                    hp, yc = k.blk(hprev, c), k.blk(y16[l], c)
+                    hp[:, 1:] = yc[:, :-1]
+                    if c:
+                        hp[:, 0] = k.blk(y16[l], c - 1)[:, -1]
+                    else:
+                        hp[:, 0].zero_()
             dx = ops.mm_nn(dg16, P[l][0], "bf16", dy16=dg16) if (l > 0 or ctx.needs_input_grad[0]) else None
             grads[6 * l + 0] = ops.mm_tn(dg16, x16[l], "bf16", dy16=dg16, x16=x16[l])
             grads[6 * l + 1] = ops.mm_tn(dg16, hprev, "bf16", dy16=dg16, x16=hprev)

@@ -334,6 +334,65 @@ def lstm_tc_bwd(dy, gates, cseq, c0, whhT16, dhT, dcT, out=None):
     return dg16, dh0, dc0
 
 
+# ---- cluster / tcgen05 recurrent kernels (csrc/lstm_c4.cu) ------------------------------------------
+_c4_ok = {}
+
+
+def lstm_c4_supported(B, H):
+    """True when eb_lstm_c4_* can run this layer: H % 256 == 0, H <= 1024 and all clusters co-resident."""
+    v = _c4_ok.get(H)
+    if v is None:
+        v = _c4_ok[H] = bool(lib().eb_lstm_c4_supported(B, H))
+    return v
+
+
+def _lstm_c4_scratch(B, H, device):
+    key = ("c4", H, device, _s())     # one exchange buffer + barrier block per stream: kernels of two layers overlap
+    t = _scratch.get(key)
+    if t is None:
+        t = torch.zeros(lib().eb_lstm_c4_scratch_bytes(B, H), dtype=torch.uint8, device=device)
+        _scratch[key] = t
+    return t
+
+
+def lstm_c4_save_buffers(B, T, H, device):
+    """(gsave, csave): CTA-private layout of the forward saves (bf16 gates, fp32 cell states)."""
+    return (torch.empty(lib().eb_lstm_c4_gsave_bytes(B, T, H), dtype=torch.uint8, device=device),
+            torch.empty(lib().eb_lstm_c4_csave_bytes(B, T, H), dtype=torch.uint8, device=device))
+
+
+def lstm_c4_fwd(xg, whh16, h0, c0, save, out=None):
+    """out = (y, hprev16, hT, cT) preallocated, or None.  Returns (y, hprev16, hT, cT, gsave | None, csave | None);
+    hprev16[:, t] = bf16(h_{t-1}) (frame 0 = h0) is the operand of the dW_hh GEMM."""
+    B, T, H4 = xg.shape
+    H = H4 // 4
+    dev = xg.device
+    if out is not None:
+        y, hprev16, hT, cT = out
+    else:
+        y = torch.empty(B, T, H, dtype=f32, device=dev)
+        hprev16 = torch.empty(B, T, H, dtype=bf16, device=dev) if save else None
+        hT = torch.empty(B, H, dtype=f32, device=dev)
+        cT = torch.empty(B, H, dtype=f32, device=dev)
+    gsave, csave = lstm_c4_save_buffers(B, T, H, dev) if save else (None, None)
+    with _timed("lstm_tc_fwd", 1, 0.0, 2.0 * B * T * 4 * H * H):
+        check(lib().eb_lstm_c4_fwd(_p(xg), _p(whh16), _p(h0), _p(c0), _p(y), _p(hprev16), _p(hT), _p(cT), _p(gsave),
+                                   _p(csave), _p(_lstm_c4_scratch(B, H, dev)), B, T, H, _s()), "eb_lstm_c4_fwd")
+    return y, hprev16, hT, cT, gsave, csave
+
+
+def lstm_c4_bwd(dy, gsave, csave, c0, whhT16, dhT, dcT, out=None):
+    B, T, H = dy.shape
+    dev = dy.device
+    dg16 = out if out is not None else torch.empty(B, T, 4 * H, dtype=bf16, device=dev)
+    dh0 = torch.empty(B, H, dtype=f32, device=dev)
+    dc0 = torch.empty(B, H, dtype=f32, device=dev)
+    with _timed("lstm_tc_bwd", 1, 0.0, 2.0 * B * T * 4 * H * H):
+        check(lib().eb_lstm_c4_bwd(_p(dy), _p(gsave), _p(csave), _p(c0), _p(whhT16), _p(dhT), _p(dcT), _p(dg16),
+                                   _p(dh0), _p(dc0), _p(_lstm_c4_scratch(B, H, dev)), B, T, H, _s()), "eb_lstm_c4_bwd")
+    return dg16, dh0, dc0
+
+
 def transpose_to_bf16(x):
     """x [rows, cols] (fp32 or bf16) -> bf16 [cols, rows]."""
     rows, cols = x.shape
@@ -445,6 +504,12 @@ def rnnt_loss_bwd_bf16(logits16, labels, xlen, ylen, blank, ws, gscale, host_sca
 def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
     check(lib().eb_adam_step(_p(p), _p(g), _p(m), _p(v), p.numel(), lr, beta1, beta2, eps, weight_decay, step,
                              grad_scale, _s()), "eb_adam_step")
+
+
+def adam_step_ex(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0, sumsq=None, max_norm=0.0,
+                 adamw=False):
+    check(lib().eb_adam_step_ex(_p(p), _p(g), _p(m), _p(v), p.numel(), lr, beta1, beta2, eps, weight_decay, step,
+                                grad_scale, _p(sumsq), float(max_norm or 0.0), int(adamw), _s()), "eb_adam_step_ex")
 
 
 def sumsq(x, out):

@@ -13,7 +13,13 @@ from . import ops
 
 
 class FlatAdam:
-    def __init__(self, module, lr=5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+    """torch.optim.Adam over the flat bucket.  ``step(grad_scale, lr, max_norm)``: grad_scale multiplies every
+    gradient (1 / loss_scale, 1 / accumulation steps); max_norm applies ``clip_grad_norm_`` semantics on the
+    device (cli/baseline.py:239-245) with no host read of the norm; with clipping or loss scaling active a
+    non-finite gradient norm skips the update (apex's overflow rule).  ``adamw=True`` selects the reference's own
+    AdamW update (modules/optimizer.py:195-292)."""
+
+    def __init__(self, module, lr=5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, adamw=False):
         params = [p for p in module.parameters() if p.requires_grad]
         if not params:
             raise ValueError("no parameters")
@@ -37,7 +43,7 @@ class FlatAdam:
                 p.data = self.flat_params[off:off + k].view(p.shape)
                 p.grad = self.flat_grads[off:off + k].view(p.shape)
         self.params = params
-        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.lr, self.betas, self.eps, self.weight_decay, self.adamw = lr, betas, eps, weight_decay, adamw
         self.step_count = 0
         self._norm = torch.zeros(1, dtype=torch.float32, device=dev)
 
@@ -53,7 +59,24 @@ class FlatAdam:
         ops.sumsq(self.flat_grads, self._norm)
         return self._norm.sqrt()
 
-    def step(self, grad_scale=1.0, lr=None):
+    def step(self, grad_scale=1.0, lr=None, max_norm=None, check_overflow=False):
         self.step_count += 1
-        ops.adam_step(self.flat_params, self.flat_grads, self.m, self.v, self.lr if lr is None else lr,
-                      self.betas[0], self.betas[1], self.eps, self.weight_decay, self.step_count, grad_scale)
+        lr = self.lr if lr is None else lr
+        if max_norm or check_overflow or self.adamw:
+            ss = None
+            if max_norm or check_overflow:
+                self._norm.zero_()
+                ops.sumsq(self.flat_grads, self._norm)
+                ss = self._norm
+            ops.adam_step_ex(self.flat_params, self.flat_grads, self.m, self.v, lr, self.betas[0], self.betas[1],
+                             self.eps, self.weight_decay, self.step_count, grad_scale, ss, max_norm or 0.0, self.adamw)
+        else:
+            ops.adam_step(self.flat_params, self.flat_grads, self.m, self.v, lr, self.betas[0], self.betas[1],
+                          self.eps, self.weight_decay, self.step_count, grad_scale)
+
+
+class FlatAdamW(FlatAdam):
+    """The reference's AdamW (modules/optimizer.py:195-292) over the flat bucket."""
+
+    def __init__(self, module, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        super().__init__(module, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, adamw=True)

@@ -103,6 +103,26 @@ int eb_lstm_tc_bwd(const float* dy, const float* gates, const float* cseq, const
                    const void* whhT16, const float* dhT, const float* dcT, void* dg16, float* dh0, float* dc0,
                    void* scratch, int B, int T, int H, void* stream);
 
+/* ---- LSTM layer on tcgen05 tensor cores inside thread-block clusters (bf16 mode; H % 256 == 0, H <= 1024) ----
+ * csrc/lstm_c4.cu: W_hh slices resident in shared memory, h / dG exchanged through L2 with TMA pulls, partial gate
+ * sums reduced across a cluster through distributed shared memory.  Same cell semantics as eb_lstm_tc_* with a
+ * CTA-private layout of the forward saves:
+ *   gsave: post-activation gates in bf16, csave: cell states in fp32, sizes from eb_lstm_c4_{g,c}save_bytes;
+ *   hprev16 [B,T,H] bf16 = h_{t-1} for every step (frame 0 = h0): the operand of the dW_hh GEMM (optional).
+ * eb_lstm_c4_supported also checks that all clusters of a launch are co-resident (cooperative cluster launch). */
+int eb_lstm_c4_supported(int B, int H);
+int eb_lstm_c4_max_clusters(int H, int which);        /* diagnostic: co-resident clusters (0 fwd, 4 / 8 bwd) */
+int eb_lstm_c4_bwd_cluster(int H);                      /* cluster size the BPTT kernel uses (8 / 4), 0 = cannot run */
+int eb_lstm_c4_set_trace(void* dev_buf, int steps);     /* debug: per-stage clock64 stamps of CTA 0 ([steps][16] int64) */
+size_t eb_lstm_c4_scratch_bytes(int B, int H);
+size_t eb_lstm_c4_gsave_bytes(int B, int T, int H);
+size_t eb_lstm_c4_csave_bytes(int B, int T, int H);
+int eb_lstm_c4_fwd(const float* xg, const void* whh16, const float* h0, const float* c0, float* y, void* hprev16,
+                   float* hT, float* cT, void* gsave, void* csave, void* scratch, int B, int T, int H, void* stream);
+int eb_lstm_c4_bwd(const float* dy, const void* gsave, const void* csave, const float* c0, const void* whhT16,
+                   const float* dhT, const float* dcT, void* dg16, float* dh0, float* dc0, void* scratch, int B,
+                   int T, int H, void* stream);
+
 /* ---- LayerNorm(x + res) fwd/bwd, TimeReduction, Embedding -------------------------------
  * rnnt/models.py:47,66-69,124 ; :21-29 ; :150-153.  *_bf16 outputs are optional side copies. */
 int eb_layernorm_fwd(const float* x, const float* res, const float* gamma, const float* beta, float* y,
@@ -150,6 +170,13 @@ int eb_cast_bf16(const float* x, void* y, long n, void* stream);
 int eb_transpose_to_bf16(const void* x, int x_bf16, void* y, long rows, long cols, void* stream);
 int eb_adam_step(float* p, const float* g, float* m, float* v, long n, float lr, float beta1,
                  float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
+/* Adam / AdamW with gradient clip and loss-scale handling on the device (no host read of the norm):
+ * sumsq = device scalar sum(g^2) of the unscaled bucket (eb_sumsq) or NULL; max_norm > 0 clips like
+ * torch.nn.utils.clip_grad_norm_ (cli/baseline.py:239-245); a non-finite norm skips the step (loss-scale overflow);
+ * adamw = 1 selects the reference's AdamW update (modules/optimizer.py:283-290). */
+int eb_adam_step_ex(float* p, const float* g, float* m, float* v, long n, float lr, float beta1, float beta2,
+                    float eps, float weight_decay, int step, float grad_scale, const float* sumsq, float max_norm,
+                    int adamw, void* stream);
 int eb_sumsq(const float* x, long n, float* out_accum, void* stream);
 
 /* ---- log-mel front end (the step before the path) ------------------------------
