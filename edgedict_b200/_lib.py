@@ -30,6 +30,7 @@ SIGNATURES = {
     "eb_lstm_tc_supported": (I, [I, I]),
     "eb_lstm_tc_scratch_bytes": (Z, [I, I]),
     "eb_lstm_tc_max_clusters": (I, [I, I]),
+    "eb_lstm_tc_set_trace": (I, [P, I]),
     "eb_lstm_tc_fwd": (I, [P, P, P, P, P, P, P, P, P, P, P, I, I, I, P]),
     "eb_lstm_tc_bwd": (I, [P, P, P, P, P, P, P, P, P, P, P, I, I, I, P]),
     "eb_lstm_c4_supported": (I, [I, I]),
@@ -39,7 +40,7 @@ SIGNATURES = {
     "eb_lstm_c4_scratch_bytes": (Z, [I, I]),
     "eb_lstm_c4_gsave_bytes": (Z, [I, I, I]),
     "eb_lstm_c4_csave_bytes": (Z, [I, I, I]),
-    "eb_lstm_c4_fwd": (I, [P, P, P, P, P, P, P, P, P, P, P, I, I, I, P]),
+    "eb_lstm_c4_fwd": (I, [P, P, P, P, P, P, P, P, P, P, P, P, P, I, I, I, P]),
     "eb_lstm_c4_bwd": (I, [P, P, P, P, P, P, P, P, P, P, P, I, I, I, P]),
     "eb_layernorm_fwd": (I, [P, P, P, P, P, P, P, P, L, I, F, P]),
     "eb_layernorm_bwd": (I, [P, P, P, P, P, P, P, P, P, L, I, P]),

@@ -93,37 +93,13 @@ struct C4FwdP {
     uint4* gsave;                 // [T][H/8][128] post-activation gates, bf16 (i0 i1 f0 f1 g0 g1 o0 o1); may be null
     float2* csave;                // [T][H/8][128] cell states; may be null
     __nv_bfloat16* hx;            // [2][NB][H] exchange
-    unsigned* bar;                // grid barrier: counter (mode bit 0 clear) or one epoch flag per CTA (bit 0 set)
+    unsigned* bar;                // grid barrier counter (one flag per CTA + a polling warp measured 1000 cycles SLOWER)
     long long* trace;             // debug: [steps][16] clock64 stamps of CTA 0 (eb_lstm_c4_set_trace), else null
     int trace_steps;
-    int mode;                     // experiments (EDGEDICT_C4_MODE): bit 0 flag barrier, bit 1 cp.async pull
+    float* gates_std; float* cseq_std;   // optional saves in the layout of eb_lstm_tc_bwd: [B,T,4H] gates, [B,T,H] cells (fp32)
     int B, T, H;
 };
 
-// Flag barrier: CTA c publishes epoch e by storing e to flags[c] (after its fence); a waiting WARP reads all flags
-// with 16-byte loads (4 flags per lane and round, up to 128 CTAs per round) and passes when none is behind.
-// No read-modify-write on a shared line: 128 same-address atomics serialise in the L2 atomic unit.
-__device__ __forceinline__ void flag_wait_warp(const unsigned* flags, unsigned ncta, unsigned epoch) {
-    const int lane = threadIdx.x & 31;
-    unsigned spins = 0;
-    while (true) {
-        bool ok = true;
-        for (unsigned base = 0; base < ncta; base += 128) {
-            const unsigned i = base + lane * 4;
-            if (i < ncta) {
-                uint4 v;
-                asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(flags + i) : "memory");
-                ok = ok && (int)(v.x - epoch) >= 0 && (int)(v.y - epoch) >= 0 && (int)(v.z - epoch) >= 0 && (int)(v.w - epoch) >= 0;
-            }
-        }
-        if (__all_sync(0xffffffffu, ok)) break;
-        if (++spins > (1u << 24)) {
-            if (lane == 0) printf("[edgedict_b200] lstm_c4: flag barrier timeout (block %d epoch %u)\n", blockIdx.x, epoch);
-            __trap();
-        }
-    }
-    asm volatile("fence.acq_rel.gpu;" ::: "memory");
-}
 __device__ __forceinline__ void cp_async16(uint32_t saddr, const void* gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(saddr), "l"(gmem) : "memory");
 }
@@ -191,12 +167,7 @@ __global__ void __launch_bounds__(NGT, 2) lstm_c4_fwd_kernel(C4FwdP p) {
         if (own && p.hprev16) *reinterpret_cast<uint32_t*>(p.hprev16 + (size_t)b * T * H + j) = hp;
     }
     __syncthreads();
-    const bool flagbar = p.mode & 1, cpasync = p.mode & 2;
-    if (tid == 0) {
-        __threadfence();
-        if (flagbar) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(p.bar + cta), "r"(1u) : "memory");
-        else atomicAdd(p.bar, 1u);
-    }
+    if (tid == 0) { __threadfence(); atomicAdd(p.bar, 1u); }
     const float* xgp = p.xg + (size_t)b * T * 4 * H + j;
     float2 xr[4];
 #pragma unroll
@@ -217,45 +188,23 @@ __global__ void __launch_bounds__(NGT, 2) lstm_c4_fwd_kernel(C4FwdP p) {
     for (int t = 0; t < T; ++t) {
         const uint32_t ph = (uint32_t)(t & 1);
         // ---- grid barrier: every CTA has published h_{t-1}; one poller, then the block
-        if (flagbar) { if (warp == 0) flag_wait_warp(p.bar, ncta, (unsigned)(t + 1)); }
-        else if (tid == 0) spin_wait_ge(p.bar, (unsigned)(t + 1) * ncta);
+        if (tid == 0) spin_wait_ge(p.bar, (unsigned)(t + 1) * ncta);
         __syncthreads();
         if (tid == 0) C4_STAMP(t, 0);
         // ---- A. pull this CTA's K slice of h_{t-1} (L2 -> registers -> swizzled shared tile)
         {
             const __nv_bfloat16* src = p.hx + (size_t)((t + 1) & 1) * xstride + (size_t)rank * KS;
-            uint4 v[8];
-            if (cpasync) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    if (i < NLD) {
-                        int row, cc;
-                        if (regular) { row = rw0 + i * rstep; cc = cc0; }
-                        else { const int q = i * NGT + tid; row = q / CPR; cc = q - row * CPR; }
-                        cp_async16(sb + (uint32_t)((cc >> 3) * 4096 + row * 128 + (((cc & 7) ^ (row & 7)) << 4)), src + (size_t)row * H + cc * 8);
-                    }
-                }
-                asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
-            } else {
+            // cp.async straight into the swizzled tile (register staging + st.shared measured 450 cycles slower)
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 if (i < NLD) {
                     int row, cc;
                     if (regular) { row = rw0 + i * rstep; cc = cc0; }
                     else { const int q = i * NGT + tid; row = q / CPR; cc = q - row * CPR; }
-                    v[i] = ld_cg16(src + (size_t)row * H + cc * 8);
+                    cp_async16(sb + (uint32_t)((cc >> 3) * 4096 + row * 128 + (((cc & 7) ^ (row & 7)) << 4)), src + (size_t)row * H + cc * 8);
                 }
             }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                if (i < NLD) {
-                    int row, cc;
-                    if (regular) { row = rw0 + i * rstep; cc = cc0; }
-                    else { const int q = i * NGT + tid; row = q / CPR; cc = q - row * CPR; }
-                    st_shared_f4(sb + (uint32_t)((cc >> 3) * 4096 + row * 128 + (((cc & 7) ^ (row & 7)) << 4)), v[i].x, v[i].y, v[i].z, v[i].w);
-                }
-            }
-            }
+            asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
             if (tid == 0) C4_STAMP(t, 9);
             fence_proxy_async_smem();
         }
@@ -323,8 +272,7 @@ __global__ void __launch_bounds__(NGT, 2) lstm_c4_fwd_kernel(C4FwdP p) {
             C4_STAMP(t, 7);
             __threadfence();
             C4_STAMP(t, 8);
-            if (flagbar) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(p.bar + cta), "r"((unsigned)(t + 2)) : "memory");
-            else atomicAdd(p.bar, 1u);
+            atomicAdd(p.bar, 1u);
         }
         // everything below overlaps the other CTAs' progress towards the barrier
         if (own) {
@@ -333,6 +281,14 @@ __global__ void __launch_bounds__(NGT, 2) lstm_c4_fwd_kernel(C4FwdP p) {
             const size_t si = ((size_t)t * NC + cta) * NGT + tid;
             if (p.gsave) p.gsave[si] = make_uint4(pack2(i0, i1), pack2(f0, f1), pack2(g0, g1), pack2(o0, o1));
             if (p.csave) p.csave[si] = make_float2(c0v, c1v);
+            if (p.gates_std) {
+                float* gp = p.gates_std + oy * 4 - 3 * (size_t)j;          // ((b*T + t) * 4H) + j
+                *reinterpret_cast<float2*>(gp) = make_float2(i0, i1);
+                *reinterpret_cast<float2*>(gp + H) = make_float2(f0, f1);
+                *reinterpret_cast<float2*>(gp + 2 * (size_t)H) = make_float2(g0, g1);
+                *reinterpret_cast<float2*>(gp + 3 * (size_t)H) = make_float2(o0, o1);
+            }
+            if (p.cseq_std) *reinterpret_cast<float2*>(p.cseq_std + oy) = make_float2(c0v, c1v);
             if (t == T - 1) {
                 *reinterpret_cast<float2*>(p.hT + (size_t)b * H + j) = make_float2(hn0, hn1);
                 *reinterpret_cast<float2*>(p.cT + (size_t)b * H + j) = make_float2(c0v, c1v);
@@ -670,8 +626,8 @@ EB_API size_t eb_lstm_c4_csave_bytes(int B, int T, int H) { return (size_t)((B +
 // xg [B,T,4H] fp32; whh16 [4H,H] bf16.  y [B,T,H] fp32; hprev16 [B,T,H] bf16 (h_{t-1}; optional); gsave / csave as sized
 // above (optional).  B > 32 runs as batch tiles of 32 (independent utterances), one launch per tile.
 EB_API int eb_lstm_c4_fwd(const float* xg, const void* whh16, const float* h0, const float* c0, float* y,
-                          void* hprev16, float* hT, float* cT, void* gsave, void* csave, void* scratch, int B, int T,
-                          int H, void* stream) {
+                          void* hprev16, float* hT, float* cT, void* gsave, void* csave, float* gates_std,
+                          float* cseq_std, void* scratch, int B, int T, int H, void* stream) {
     if (!xg || !whh16 || !y || !hT || !cT || !scratch || T <= 0 || !c4_shape_ok(B, H)) return EB_ERR_INVALID;
     if ((reinterpret_cast<uintptr_t>(whh16) & 15) || (reinterpret_cast<uintptr_t>(xg) & 7) || (reinterpret_cast<uintptr_t>(y) & 7))
         return EB_ERR_INVALID;
@@ -696,7 +652,8 @@ EB_API int eb_lstm_c4_fwd(const float* xg, const void* whh16, const float* h0, c
         p.bar = reinterpret_cast<unsigned*>(base);
         p.B = (B - b0 < NB) ? (B - b0) : NB; p.T = T; p.H = H;
         p.trace = g_trace; p.trace_steps = g_trace_steps;
-        { const char* e = getenv("EDGEDICT_C4_MODE"); p.mode = e ? atoi(e) : 0; }
+        p.gates_std = gates_std ? gates_std + (size_t)b0 * T * 4 * H : nullptr;
+        p.cseq_std = cseq_std ? cseq_std + (size_t)b0 * T * H : nullptr;
         EB_CUDA(cudaMemsetAsync(scratch, 0, C4_HDR, st));
         if (!launch_clustered(lstm_c4_fwd_kernel, H / UPC, NGT, 4, smem, st, p)) return EB_ERR_CUDA;
     }

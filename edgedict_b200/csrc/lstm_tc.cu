@@ -282,8 +282,15 @@ struct BwdP {
     unsigned* bar;
     unsigned* gbar;               // per-group counters (non-cluster variant)
     float* pglob;                 // [H/(8*CS)][CS][8*CS][NB] partial tiles in L2 (non-cluster variant)
+    long long* trace; int trace_steps;   // debug: clock64 stamps of CTA 0 (eb_lstm_tc_set_trace)
     int B, T, H;
 };
+#define TC_STAMP(step, s)                                                                          \
+    do {                                                                                           \
+        if (p.trace && blockIdx.x == 0 && tid == 0 && (step) < p.trace_steps) p.trace[(size_t)(step) * 16 + (s)] = clock64(); \
+    } while (0)
+long long* g_tc_trace = nullptr;
+int g_tc_trace_steps = 0;
 
 // REMAP selects the phase-A thread -> (unit, batch row) map:
 //   false (default, every measurement of round 1): unit = warp, row = lane.  A warp-wide load of a saved gate then
@@ -367,6 +374,7 @@ __global__ void __launch_bounds__(NW * 32, 1) lstm_tc_bwd_kernel(BwdP p) {
 
     for (int t = T - 1; t >= 0; --t) {
         __nv_bfloat16* gcur = p.gx + (t & 1) * xstride;
+        TC_STAMP(T - 1 - t, 0);
         // ---- phase A: gate gradients of step t for the owned (unit, batch)
         {
             float da[4] = {0.f, 0.f, 0.f, 0.f};
@@ -398,7 +406,9 @@ __global__ void __launch_bounds__(NW * 32, 1) lstm_tc_bwd_kernel(BwdP p) {
         }
         __syncthreads();
         ++epoch;
+        TC_STAMP(T - 1 - t, 1);
         if (tid == 0) { __threadfence(); atomicAdd(p.bar, 1u); }
+        TC_STAMP(T - 1 - t, 2);
         if (tid < NB * 4) {   // off the critical path: dG_t in the standard gate-major layout, 16-byte stores
             const int b = tid >> 2, c = tid & 3;
             const int jb = js * JS + rs * UPC;
@@ -407,9 +417,12 @@ __global__ void __launch_bounds__(NW * 32, 1) lstm_tc_bwd_kernel(BwdP p) {
         }
         EB_PREFETCH(t - 1)                                   // overlaps the wait
         if (tid == 0) spin_wait_ge(p.bar, epoch * ncta);     // one poller per CTA (see forward kernel)
+        TC_STAMP(T - 1 - t, 3);
         __syncthreads();
+        TC_STAMP(T - 1 - t, 4);
         // ---- phase B: partial dh_rec[unit (JS), batch] over this CTA's K-slice of dG_t
         warp_pull(gs + ks0 * 16, KP, gcur + r0 + ks0 * 16, H4, myks * 2, NB);
+        TC_STAMP(T - 1 - t, 5);
         float acc[MT][4][4];
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt)
@@ -431,6 +444,7 @@ __global__ void __launch_bounds__(NW * 32, 1) lstm_tc_bwd_kernel(BwdP p) {
                 }
             }
         }
+        TC_STAMP(T - 1 - t, 6);
         // cross-warp reduction: red[w][slot][lane], slot = mt*16 + nt*4 + i
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt)
@@ -439,6 +453,7 @@ __global__ void __launch_bounds__(NW * 32, 1) lstm_tc_bwd_kernel(BwdP p) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) red[(w * SLOTS + mt * 16 + nt * 4 + i) * 32 + l] = acc[mt][nt][i];
         __syncthreads();
+        TC_STAMP(T - 1 - t, 7);
         // SLOTS/NW slots per thread: slot -> (mt = slot/16, nt = (slot/4)%4, i = slot%4)
 #pragma unroll
         for (int q = 0; q < SLOTS / NW; ++q) {
@@ -452,9 +467,11 @@ __global__ void __launch_bounds__(NW * 32, 1) lstm_tc_bwd_kernel(BwdP p) {
             if (CLUSTER) part[((t & 1) * JS + unit) * NB + bcol] = s;
             else p.pglob[((((size_t)(t & 1) * gridDim.x / CS + js) * CS + rs) * JS + unit) * NB + bcol] = s;
         }
+        TC_STAMP(T - 1 - t, 8);
         if (CLUSTER) {
             cg::cluster_group cluster = cg::this_cluster();
             cluster.sync();                                 // all CS partial tiles of the group are visible
+            TC_STAMP(T - 1 - t, 9);
             float s = 0.f;
 #pragma unroll
             for (int c = 0; c < CS; ++c) {
@@ -462,6 +479,7 @@ __global__ void __launch_bounds__(NW * 32, 1) lstm_tc_bwd_kernel(BwdP p) {
                 s += rp[((t & 1) * JS + rs * UPC + uu) * NB + bb];
             }
             dh = s;                                          // dh_rec for (unit j, batch l) at step t-1
+            TC_STAMP(T - 1 - t, 10);
             // `part` is double buffered by step parity: a buffer is rewritten two steps later, i.e.
             // after another cluster.sync() that every reader passes only when done reading.
         } else {
@@ -570,6 +588,13 @@ int pick_cs(int H) {
 
 }  // namespace
 
+// debug: clock64 stamps of CTA 0 of the BPTT kernel for the first `steps` steps of subsequent launches ([steps][16] int64)
+EB_API int eb_lstm_tc_set_trace(void* dev_buf, int steps) {
+    g_tc_trace = reinterpret_cast<long long*>(dev_buf);
+    g_tc_trace_steps = dev_buf ? steps : 0;
+    return EB_OK;
+}
+
 EB_API int eb_lstm_tc_supported(int B, int H) { return tc_ok(B, H) ? 1 : 0; }
 
 EB_API size_t eb_lstm_tc_scratch_bytes(int B, int H) {
@@ -646,6 +671,7 @@ EB_API int eb_lstm_tc_bwd(const float* dy, const float* gates, const float* cseq
         p.gx = reinterpret_cast<__nv_bfloat16*>(base + TC_HDR);
         p.pglob = reinterpret_cast<float*>(base + TC_HDR + sizeof(__nv_bfloat16) * (size_t)2 * NB * 4 * H);
         p.B = nb; p.T = T; p.H = H;
+        p.trace = g_tc_trace; p.trace_steps = g_tc_trace_steps;
         EB_CUDA(cudaMemsetAsync(scratch, 0, TC_HDR + sizeof(__nv_bfloat16) * (size_t)2 * NB * 4 * H, st));
         bool launched = false;
         if (cs == 8) launched = launch_cluster<8>(p, H, st);

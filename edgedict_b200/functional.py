@@ -123,7 +123,8 @@ class LSTMLayer(torch.autograd.Function):
         c4 = precision == "bf16" and ops.lstm_c4_supported(B, H)
         if c4:
             # cluster / tcgen05 kernels: saves in their CTA-private layout, y16 IS the h_{t-1}-shifted copy
-            y, y16, hT, cT, gates, cseq = ops.lstm_c4_fwd(xg, ops.cast_bf16(_c(w_hh)), h0c, c0c, need)
+            y, y16, hT, cT, gates, cseq = ops.lstm_c4_fwd(xg, ops.cast_bf16(_c(w_hh)), h0c, c0c, need,
+                                                          std_saves=None if ops.C4_BWD else True)
         elif tc:
             y, y16, hT, cT, gates, cseq = ops.lstm_tc_fwd(xg, ops.cast_bf16(_c(w_hh)), h0c, c0c, need)
         else:
@@ -131,7 +132,7 @@ class LSTMLayer(torch.autograd.Function):
             y16 = None
         if need:
             ctx.save_for_backward(x2 if x16 is None else x16, h0c, c0c, w_ih, w_hh, y16 if (tc or c4) else y, gates, cseq)
-            ctx.precision, ctx.dims, ctx.tc, ctx.c4 = precision, (B, T, I, H), tc, c4
+            ctx.precision, ctx.dims, ctx.tc, ctx.c4, ctx.c4_bwd = precision, (B, T, I, H), tc, c4, c4 and ops.C4_BWD
         return y, hT, cT
 
     @staticmethod
@@ -146,10 +147,10 @@ class LSTMLayer(torch.autograd.Function):
             raise RuntimeError("LSTMLayer.backward ran twice on the same graph: the saved gates are overwritten in "
                                "place by the first pass (retain_graph is not supported by this node)")
         ctx.consumed = True
-        if ctx.c4:
+        if ctx.c4_bwd:
             dg16, dh0, dc0 = ops.lstm_c4_bwd(dy, gates, cseq, c0, ops.transpose_to_bf16(_c(w_hh)), dhT, dcT)
             dg2 = dg16.view(B * T, 4 * H)
-        elif ctx.tc:
+        elif ctx.tc or ctx.c4:
             dg16, dh0, dc0 = ops.lstm_tc_bwd(dy, gates, cseq, c0, ops.transpose_to_bf16(_c(w_hh)), dhT, dcT)
             dg2 = dg16.view(B * T, 4 * H)
         else:
@@ -272,6 +273,7 @@ class LSTMStack(torch.autograd.Function):
         C = len(plan[0])
         need = any(ctx.needs_input_grad)
         c4 = ops.lstm_c4_supported(B, H)
+        c4b = c4 and ops.C4_BWD                              # saves in lstm_c4's own layout, BPTT through lstm_c4
         ck = [_Chunks(B, lens) for lens in plan]
         P = [params[6 * l:6 * l + 6] for l in range(L)]
         wih16 = [ops.cast_bf16(_c(p[0])) for p in P]
@@ -285,8 +287,8 @@ class LSTMStack(torch.autograd.Function):
             k, kn = ck[l], ck[l + 1]
             y[l] = k.new(H, f32, dev)
             y16[l] = k.new(H, bf16, dev) if (need or not c4) else None     # c4: holds h_{t-1} (the dW_hh operand)
-            gates[l] = k.new(4 * H, f32, dev) if (need and not c4) else None
-            cseq[l] = k.new(H, f32, dev) if (need and not c4) else None
+            gates[l] = k.new(4 * H, f32, dev) if (need and not c4b) else None
+            cseq[l] = k.new(H, f32, dev) if (need and not c4b) else None
             mean[l], rstd[l] = k.new(0, f32, dev), k.new(0, f32, dev)
             xs[l + 1] = kn.new(H, f32, dev)
             z[l] = k.new(H, f32, dev) if reductions[l] else xs[l + 1]
@@ -317,8 +319,9 @@ class LSTMStack(torch.autograd.Function):
                     if c4:
                         r = ops.lstm_c4_fwd(xg.view(B, Tc, 4 * H), whh16[l], hT[l, c - 1] if c else None,
                                             cT[l, c - 1] if c else None, need,
-                                            out=(k.blk(y[l], c), k.blk(y16[l], c) if need else None, hT[l, c], cT[l, c]))
-                        if need:
+                                            out=(k.blk(y[l], c), k.blk(y16[l], c) if need else None, hT[l, c], cT[l, c]),
+                                            std_saves=None if (c4b or not need) else (k.blk(gates[l], c), k.blk(cseq[l], c)))
+                        if need and c4b:
                             c4saves[l][c] = (r[4], r[5])
                             r[4].record_stream(main)
                             r[5].record_stream(main)
@@ -344,12 +347,12 @@ class LSTMStack(torch.autograd.Function):
             LSTMStack.collect.extend(ck[l + 1].gather(xs[l + 1]) for l in range(L))
         hT_last, cT_last = hT[:, C - 1].contiguous(), cT[:, C - 1].contiguous()
         if need:
-            if c4:
+            if c4b:
                 gates = [torch.empty(0, device=dev)] * L
                 cseq = [torch.empty(0, device=dev)] * L
-            flat_saves = [t for row in c4saves for pair in row for t in pair] if c4 else []
+            flat_saves = [t for row in c4saves for pair in row for t in pair] if c4b else []
             ctx.save_for_backward(*params, hT, cT, *x16[:L], *xs[1:L], *y, *y16, *gates, *cseq, *mean, *rstd, *flat_saves)
-            ctx.cfg, ctx.dims, ctx.c4 = cfg, (B, T, I0, H, L, C), c4
+            ctx.cfg, ctx.dims, ctx.c4, ctx.c4b = cfg, (B, T, I0, H, L, C), c4, c4b
         ctx.mark_non_differentiable(hT_last, cT_last)
         return out, hT_last, cT_last
 
@@ -364,7 +367,7 @@ class LSTMStack(torch.autograd.Function):
         x16, sv = sv[:L], sv[L:]
         xs, sv = [None] + sv[:L - 1], sv[L - 1:]
         y, y16, gates, cseq, mean, rstd = (sv[i * L:(i + 1) * L] for i in range(6))
-        c4 = ctx.c4
+        c4, c4b = ctx.c4, ctx.c4b
         flat_saves = sv[6 * L:]
         if getattr(ctx, "consumed", False):
             raise RuntimeError("LSTMStack.backward ran twice on the same graph (retain_graph is not supported)")
@@ -385,17 +388,19 @@ class LSTMStack(torch.autograd.Function):
             whhT16 = ops.transpose_to_bf16(_c(P[l][1]))
             dg16 = k.new(4 * H, bf16, dev)
             dh = dc = None
-            if c4:
+            if c4b:
                 hprev = y16[l]                                # written by the forward kernel
                 for c in range(C - 1, -1, -1):
                     gs, cs = flat_saves[2 * (l * C + c)], flat_saves[2 * (l * C + c) + 1]
                     _, dh, dc = ops.lstm_c4_bwd(k.blk(dz, c), gs, cs, cT[l, c - 1] if c else None, whhT16, dh, dc,
                                                 out=k.blk(dg16, c))
             else:
-                hprev = k.new(H, bf16, dev)
+                hprev = y16[l] if c4 else k.new(H, bf16, dev)  # c4 forward: h_{t-1} already written by the kernel
                 for c in range(C - 1, -1, -1):
                     _, dh, dc = ops.lstm_tc_bwd(k.blk(dz, c), k.blk(gates[l], c), k.blk(cseq[l], c),
                                                 cT[l, c - 1] if c else None, whhT16, dh, dc, out=k.blk(dg16, c))
+                    if c4:
+                        continue
                     hp, yc = k.blk(hprev, c), k.blk(y16[l], c)
                     hp[:, 1:] = yc[:, :-1]
                     if c:
@@ -544,6 +549,10 @@ class JointLoss(torch.autograd.Function):
     @staticmethod
     def backward(ctx, go, _gc):
         hid, he2, hd2, w1, w2, logits, labels, act_lens, label_lens, ws = ctx.saved_tensors
+        if getattr(ctx, "consumed", False):
+            raise RuntimeError("JointLoss.backward ran twice on the same graph: the gradient is written in place over "
+                               "the saved logits (retain_graph is not supported by this node)")
+        ctx.consumed = True
         B, T, U, E, Dd, J, V = ctx.dims
         p = ctx.precision
         g = _c(go.to(f32)).view(-1)

@@ -361,9 +361,14 @@ def lstm_c4_save_buffers(B, T, H, device):
             torch.empty(lib().eb_lstm_c4_csave_bytes(B, T, H), dtype=torch.uint8, device=device))
 
 
-def lstm_c4_fwd(xg, whh16, h0, c0, save, out=None):
+C4_BWD = __import__("os").environ.get("EDGEDICT_LSTM_C4_BWD", "0") != "0"   # BPTT through lstm_c4 (else lstm_tc's kernel)
+
+
+def lstm_c4_fwd(xg, whh16, h0, c0, save, out=None, std_saves=None):
     """out = (y, hprev16, hT, cT) preallocated, or None.  Returns (y, hprev16, hT, cT, gsave | None, csave | None);
-    hprev16[:, t] = bf16(h_{t-1}) (frame 0 = h0) is the operand of the dW_hh GEMM."""
+    hprev16[:, t] = bf16(h_{t-1}) (frame 0 = h0) is the operand of the dW_hh GEMM.  The saves for backward are
+    either the kernels' own CTA-private layout (gsave, csave: consumed by lstm_c4_bwd) or, with
+    std_saves = (gates [B,T,4H] fp32, cseq [B,T,H] fp32) (or True to allocate them), the layout of lstm_tc_bwd."""
     B, T, H4 = xg.shape
     H = H4 // 4
     dev = xg.device
@@ -374,10 +379,18 @@ def lstm_c4_fwd(xg, whh16, h0, c0, save, out=None):
         hprev16 = torch.empty(B, T, H, dtype=bf16, device=dev) if save else None
         hT = torch.empty(B, H, dtype=f32, device=dev)
         cT = torch.empty(B, H, dtype=f32, device=dev)
-    gsave, csave = lstm_c4_save_buffers(B, T, H, dev) if save else (None, None)
+    gsave = csave = gstd = cstd = None
+    if save and std_saves is not None and std_saves is not False:
+        gstd, cstd = std_saves if isinstance(std_saves, tuple) else (torch.empty(B, T, H4, dtype=f32, device=dev),
+                                                                     torch.empty(B, T, H, dtype=f32, device=dev))
+    elif save:
+        gsave, csave = lstm_c4_save_buffers(B, T, H, dev)
     with _timed("lstm_tc_fwd", 1, 0.0, 2.0 * B * T * 4 * H * H):
         check(lib().eb_lstm_c4_fwd(_p(xg), _p(whh16), _p(h0), _p(c0), _p(y), _p(hprev16), _p(hT), _p(cT), _p(gsave),
-                                   _p(csave), _p(_lstm_c4_scratch(B, H, dev)), B, T, H, _s()), "eb_lstm_c4_fwd")
+                                   _p(csave), _p(gstd), _p(cstd), _p(_lstm_c4_scratch(B, H, dev)), B, T, H, _s()),
+              "eb_lstm_c4_fwd")
+    if gstd is not None:
+        return y, hprev16, hT, cT, gstd, cstd
     return y, hprev16, hT, cT, gsave, csave
 
 

@@ -242,10 +242,11 @@ class Transducer(nn.Module):
         """rnnt/models.py:243-269: at most one symbol per encoder frame; returns (list of id arrays
         incl. blanks, truncated by the UNSCALED xlen as the reference does, -sum log p).  The T'
         per-frame iterations run device-side in one persistent kernel (stream_engine.GreedyEngine)."""
-        from ..stream_engine import GreedyEngine
+        from ..stream_engine import GreedyEngine, param_fingerprint
         h_enc, _ = self.encoder(xs)
         B, T = h_enc.shape[0], h_enc.shape[1]
-        key = (B, T, h_enc.device)
+        # the phase program bakes raw weight pointers: re-homed parameters (FlatAdam, .to(), .float()) rebuild it
+        key = (B, T, h_enc.device, param_fingerprint(self))
         cache = self.__dict__.setdefault("_greedy_engines", {})
         eng = cache.get(key)
         if eng is None:

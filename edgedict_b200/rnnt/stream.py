@@ -16,7 +16,7 @@ import torch
 
 from .models import Transducer, convert_lightning2normal
 from .tokenizer import NUL, BOS, UNK
-from ..stream_engine import StreamEngine
+from ..stream_engine import StreamEngine, param_fingerprint
 
 
 class StreamTransducerDecoder:
@@ -34,7 +34,7 @@ class StreamTransducerDecoder:
 
 class PytorchStreamDecoder(StreamTransducerDecoder):
     def __init__(self, FLAGS, transducer=None, transform=None, tokenizer=None, device="cuda",
-                 frames_per_chunk=None):
+                 frames_per_chunk=None, input_size=None):
         self.FLAGS = FLAGS
         self.device = torch.device(device)
         if tokenizer is None:
@@ -49,6 +49,9 @@ class PytorchStreamDecoder(StreamTransducerDecoder):
                 win_length=FLAGS.win_length, hop_length=FLAGS.hop_length, delta=FLAGS.delta, cmvn=FLAGS.cmvn,
                 downsample=FLAGS.downsample, pad_to_divisible=False, T_mask=FLAGS.T_mask,
                 T_num_mask=FLAGS.T_num_mask, F_mask=FLAGS.F_mask, F_num_mask=FLAGS.F_num_mask)
+        elif input_size is None and transducer is None:
+            # a caller-supplied transform: the feature width follows the flagfile (rnnt/transforms.py:30-51)
+            input_size = FLAGS.feature_size * FLAGS.downsample * (3 if getattr(FLAGS, "delta", False) else 1)
         self.transform = transform
         if transducer is None:
             logdir = os.path.join('logs', FLAGS.name)
@@ -82,7 +85,11 @@ class PytorchStreamDecoder(StreamTransducerDecoder):
             return UNK
 
     def _build(self, n):
-        self._engine = StreamEngine(self._transducer, 1, n, unk_id=self._unk, blank=NUL)
+        # a different chunk length (a short last chunk, a changed block size) or re-homed weights need a new phase
+        # program, NOT a new utterance: the recurrent state moves over (rnnt/stream.py:94-120 carries it across
+        # arbitrary chunk lengths); only reset() starts from the primed zero state
+        st = self._engine.state() if self._engine is not None else None
+        self._engine = StreamEngine(self._transducer, 1, n, unk_id=self._unk, blank=NUL, state=st)
         self._frames = n
 
     @torch.no_grad()
@@ -94,7 +101,8 @@ class PytorchStreamDecoder(StreamTransducerDecoder):
     def decode(self, frame):
         start = time.time()
         xs = self.transform(frame).transpose(1, 2)                  # [1, n, F] log-mel, as stream.py:96
-        if self._engine is None or xs.shape[1] != self._frames:
+        if self._engine is None or xs.shape[1] != self._frames or \
+                self._engine.fingerprint != param_fingerprint(self._transducer):
             self._build(xs.shape[1])
         ids = self._engine.step(xs.to(self.device, non_blocking=True))[0].tolist()   # one D2H per chunk
         self.encoder_elapsed.append(time.time() - start)

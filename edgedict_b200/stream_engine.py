@@ -30,8 +30,16 @@ def _ptr(t, off=0):
     return None if t is None else t.data_ptr() + off * t.element_size()
 
 
+def param_fingerprint(module):
+    """Identity of the parameter storage a phase program was built over: the programs bake raw device pointers, so a
+    re-homed parameter (FlatAdam bucket, .to(), .float(), p.data = ...) must trigger a rebuild."""
+    return tuple(p.data_ptr() for p in module.parameters())
+
+
 class StreamEngine:
-    def __init__(self, transducer, n_streams, frames_per_chunk, unk_id=UNK, blank=NUL, max_ctas=0):
+    STATE = ("enc_h", "enc_c", "dec_h", "dec_c", "dec_x", "tok")
+
+    def __init__(self, transducer, n_streams, frames_per_chunk, unk_id=UNK, blank=NUL, max_ctas=0, state=None):
         assert C.sizeof(EbPhase) == lib().eb_decode_phase_size(), "EbPhase layout mismatch"
         enc, dec, joint = transducer.encoder, transducer.decoder, transducer.joint.joint
         self.dev = enc.norm.weight.device
@@ -49,6 +57,7 @@ class StreamEngine:
         self.xin, self.a0 = z(S, n, F), z(S, n, F)
         self.enc_h, self.enc_c, self.enc_htmp = z(L, S, H), z(L, S, H), z(L, S, H)
         self._keep = [p.detach() for p in transducer.parameters()]      # weights are read in place
+        self.fingerprint = param_fingerprint(transducer)
         prog = []
 
         def ph(**kw):
@@ -133,7 +142,19 @@ class StreamEngine:
         self._chunk = self._upload(chunk_prog)
         self._prime = self._upload(prog)
         self._bar = torch.zeros(64, dtype=torch.int32, device=self.dev)
-        self.reset()
+        if state is None:
+            self.reset()
+        else:
+            self.load_state(state)                      # a rebuilt program continues the utterance (rnnt/stream.py:97-98)
+
+    def state(self):
+        """The recurrent state of every stream (what PytorchStreamDecoder carries between chunks, rnnt/stream.py:78-91)."""
+        return {k: getattr(self, k).clone() for k in self.STATE}
+
+    @torch.no_grad()
+    def load_state(self, st):
+        for k in self.STATE:
+            getattr(self, k).copy_(st[k])
 
     def _upload(self, prog):
         arr = (EbPhase * len(prog))(*prog)

@@ -95,6 +95,7 @@ int eb_lstm_seq_bwd(const float* dy, const float* gates, const float* cseq, cons
  * [B,T,4H] bf16 gate-preactivation gradients. */
 int eb_lstm_tc_supported(int B, int H);
 size_t eb_lstm_tc_scratch_bytes(int B, int H);
+int eb_lstm_tc_set_trace(void* dev_buf, int steps);     /* debug: per-stage clock64 stamps of CTA 0 of the BPTT kernel */
 int eb_lstm_tc_max_clusters(int H, int cluster_size);   /* co-resident clusters of the BPTT kernel (diagnostic) */
 int eb_lstm_tc_fwd(const float* xg, const void* whh16, const float* h0, const float* c0, float* y, void* y16,
                    float* hT, float* cT, float* gates_save, float* cseq_save, void* scratch, int B, int T,
@@ -118,7 +119,8 @@ size_t eb_lstm_c4_scratch_bytes(int B, int H);
 size_t eb_lstm_c4_gsave_bytes(int B, int T, int H);
 size_t eb_lstm_c4_csave_bytes(int B, int T, int H);
 int eb_lstm_c4_fwd(const float* xg, const void* whh16, const float* h0, const float* c0, float* y, void* hprev16,
-                   float* hT, float* cT, void* gsave, void* csave, void* scratch, int B, int T, int H, void* stream);
+                   float* hT, float* cT, void* gsave, void* csave, float* gates_std, float* cseq_std, void* scratch,
+                   int B, int T, int H, void* stream);   /* gates_std / cseq_std: optional saves in eb_lstm_tc_bwd's layout */
 int eb_lstm_c4_bwd(const float* dy, const void* gsave, const void* csave, const float* c0, const void* whhT16,
                    const float* dhT, const float* dcT, void* dg16, float* dh0, float* dc0, void* scratch, int B,
                    int T, int H, void* stream);

@@ -34,6 +34,8 @@ if "check" in what:
         h0, c0 = torch.randn(B, H, device=dev) * 0.5, torch.randn(B, H, device=dev) * 0.5
         y0, y16, hT0, cT0, gates0, cseq0 = ops.lstm_tc_fwd(xg, whh16, h0, c0, True)
         y1, hp1, hT1, cT1, gs, cs = ops.lstm_c4_fwd(xg, whh16, h0, c0, True)
+        gstd, cstd = ops.lstm_c4_fwd(xg, whh16, h0, c0, True, std_saves=True)[4:]
+        print("    std saves: gates %.2e c %.2e" % (rel(gstd, gates0), rel(cstd, cseq0)))
         torch.cuda.synchronize()
         hp_ref = torch.cat([h0.bfloat16()[:, None], y16[:, :-1]], 1)
         print("fwd B%d T%d H%d: y %.2e hT %.2e cT %.2e hprev %.2e" % (B, T, H, rel(y1, y0), rel(hT1, hT0), rel(cT1, cT0),
@@ -50,9 +52,7 @@ if "check" in what:
         print("bwd B%d T%d H%d: dg %.2e dh0 %.2e dc0 %.2e" % (B, T, H, rel(dg1.float(), dg0.float()), rel(dh01, dh00),
                                                                rel(dc01, dc00)), flush=True)
 
-for mode in ([0, 1, 3] if "time" in what else []):
-    os.environ["EDGEDICT_C4_MODE"] = str(mode)
-    print("---- EDGEDICT_C4_MODE=%d" % mode)
+for mode in ([0] if "time" in what else []):
     B, T, H = 32, 500, 1024
     torch.manual_seed(0)
 
@@ -96,9 +96,7 @@ if "occ" in what:
     for H in (256, 512, 1024):
         print("H", H, "max clusters fwd/4:", lib().eb_lstm_c4_max_clusters(H, 0), "bwd/4:", lib().eb_lstm_c4_max_clusters(H, 4),
               "bwd/8:", lib().eb_lstm_c4_max_clusters(H, 8), "need", H // 32, H // 32, H // 64)
-for mode in ([0, 1, 2, 3] if "trace" in what else []):
-    os.environ["EDGEDICT_C4_MODE"] = str(mode)
-    print("---- EDGEDICT_C4_MODE=%d (bit0 flag barrier, bit1 cp.async pull)" % mode)
+for mode in ([0] if "trace" in what else []):
     B, T, H = 32, 400, 1024
     torch.manual_seed(0)
     xg = torch.randn(B, T, 4 * H, device=dev)
@@ -120,3 +118,27 @@ for mode in ([0, 1, 2, 3] if "trace" in what else []):
     per = float((t[1:, 0] - t[:-1, 0]).mean())
     print("  step period %.0f cyc = %.2f us at 1.965 GHz" % (per, per / 1965))
     print("  threadfence done -> next barrier passed: %.0f cyc" % float((t[1:, 0] - t[:-1, 8]).mean()))
+
+
+if "trace_bwd" in what:
+    B, T, H = 32, 400, 1024
+    torch.manual_seed(0)
+    xg = torch.randn(B, T, 4 * H, device=dev)
+    w = (torch.randn(4 * H, H, device=dev) / 32).bfloat16()
+    wT = w.t().contiguous()
+    y0, y16, hT0, cT0, gates0, cseq0 = ops.lstm_tc_fwd(xg, w, None, None, True)
+    dy = torch.randn_like(y0)
+    ops.lstm_tc_bwd(dy, gates0, cseq0, None, wT, None, None)
+    tr = torch.zeros(T, 16, dtype=torch.int64, device=dev)
+    lib().eb_lstm_tc_set_trace(tr.data_ptr(), T)
+    ops.lstm_tc_bwd(dy, gates0, cseq0, None, wT, None, None)
+    torch.cuda.synchronize()
+    lib().eb_lstm_tc_set_trace(None, 0)
+    t = tr.cpu().double()[50:350]
+    names = {0: "step top", 1: "phase A + exchange store + sync", 2: "threadfence + atomic", 3: "poll ok (prefetch issued before)", 4: "block sync",
+             5: "pull done (warp 0)", 6: "hmma done", 7: "red stored + sync", 8: "reduce -> part", 9: "cluster.sync", 10: "dsmem read (dh)"}
+    base = t[:, 0]
+    for i, n in names.items():
+        print("  +%7.0f cyc  %s" % (float((t[:, i] - base).mean()), n))
+    per = float((t[1:, 0] - t[:-1, 0]).mean())
+    print("  old BPTT step period %.0f cyc = %.2f us at 1.965 GHz" % (per, per / 1965))

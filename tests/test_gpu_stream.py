@@ -91,3 +91,34 @@ def test_stream_decoder_interface():
     assert dec.encoder_elapsed == []
     dec.reset()
     assert dec.decode(torch.as_tensor(z["stream_chunks"][0][None])) == ("t%d " % z["stream_tokens"][0] if z["stream_tokens"][0] >= 0 else "")
+
+
+def test_stream_state_survives_chunk_length_change_and_rehomed_weights():
+    """a chunk of a different length (short last chunk) or re-homed parameter storage rebuilds the phase
+    program but must NOT wipe the recurrent state (rnnt/stream.py:94-120 carries it across arbitrary chunks)."""
+    from edgedict_b200.rnnt.models import Transducer
+    from edgedict_b200.stream_engine import StreamEngine, param_fingerprint
+    from oracle import model_torch as mt
+    from tests.util import load_tiny
+    z, cfg, sd, _ = load_tiny()
+    m = Transducer(output_loss=False, **cfg)
+    m.load_state_dict({k: torch.as_tensor(v) for k, v in sd.items()})
+    m = m.cuda().eval()
+    sdc = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    F = cfg["input_size"]
+    g = torch.Generator().manual_seed(7)
+    lens = [4, 4, 2, 6, 2]
+    chunks = [torch.randn(1, n, F, generator=g) for n in lens]
+    st = mt.StreamState(sdc)
+    want = [mt.stream_decode(sdc, st, c) for c in chunks]
+    eng = None
+    got = []
+    for i, c in enumerate(chunks):
+        if i == 3:                                   # re-home the weights mid-utterance
+            for p in m.parameters():
+                p.data = p.data.clone()
+        if eng is None or eng.n != c.shape[1] or eng.fingerprint != param_fingerprint(m):
+            eng = StreamEngine(m, 1, c.shape[1], state=None if eng is None else eng.state())
+        ids = eng.step(c.cuda())[0].tolist()
+        got.append([t for t in ids if t != 0])
+    assert got == want
