@@ -61,6 +61,7 @@ SIGNATURES = {
     "eb_fe_preemph_pad": (I, [P, P, I, I, L, I, F, I, P]),
     "eb_fe_power": (I, [P, P, L, I, P]),
     "eb_fe_log_stack": (I, [P, P, I, I, I, I, I, I, I, I, P]),
+    "eb_fe_mask": (I, [P, P, I, I, I, I, I, F, P]),
     # warp-transducer compatible ABI (include/rnnt.h)
     "get_warprnnt_version": (I, []),
     "rnntGetStatusString": (C.c_char_p, [I]),

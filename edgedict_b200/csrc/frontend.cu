@@ -62,7 +62,29 @@ __global__ void fe_log_stack_kernel(const float* __restrict__ mel, float* __rest
     out[(long)b * Tout * W + i] = v;
 }
 
+// SpecAugment masking (rnnt/transforms.py:53-147): x [B, D1, D2]; spans [B, nmask, 2] = [start, end) along dim `axis`
+// (1: frequency rows, 2: time columns); masked elements := fill.
+__global__ void fe_mask_kernel(float* __restrict__ x, const int* __restrict__ spans, int nmask, int D1, int D2, int axis,
+                               float fill) {
+    const int b = blockIdx.y;
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)D1 * D2) return;
+    const int pos = axis == 1 ? (int)(i / D2) : (int)(i % D2);
+    const int* sp = spans + (long)b * nmask * 2;
+    bool hit = false;
+    for (int m = 0; m < nmask; ++m) hit = hit || (pos >= sp[2 * m] && pos < sp[2 * m + 1]);
+    if (hit) x[(long)b * D1 * D2 + i] = fill;
+}
+
 }  // namespace
+
+EB_API int eb_fe_mask(float* x, const int* spans, int B, int D1, int D2, int nmask, int axis, float fill, void* stream) {
+    if (!x || !spans || B <= 0 || D1 <= 0 || D2 <= 0 || nmask <= 0 || (axis != 1 && axis != 2)) return EB_ERR_INVALID;
+    dim3 grid((unsigned)(((long)D1 * D2 + 255) / 256), B);
+    fe_mask_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, spans, nmask, D1, D2, axis, fill);
+    EB_CHECK_LAUNCH();
+    return EB_OK;
+}
 
 EB_API int eb_fe_preemph_pad(const float* x, float* xp, int B, int L, long Lp, int pad, float preemph,
                              int use_preemph, void* stream) {

@@ -39,14 +39,9 @@ constexpr int UPC = 8;            // hidden units finalised per CTA
 constexpr int RP = 36;            // floats per row of the DSMEM receive tiles (16-byte aligned, conflict-free)
 // forward receive / staging tiles: [src or dest][32 rows][32 floats], 16-byte chunk c of row r stored at chunk c ^ (r & 7)
 __device__ __forceinline__ int swz(int row, int b) { return row * 32 + ((((b >> 2) ^ (row & 7)) << 2) | (b & 3)); }
-__device__ __forceinline__ void bulk_s2c(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t mbar_cluster) {
-    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(dst_cluster), "r"(src_cta), "r"(bytes), "r"(mbar_cluster) : "memory");
-}
 __device__ __forceinline__ void st_shared_f4(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" :: "r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 constexpr int NGT = 128;          // gate threads (warps 0-3); warp 4 = barrier poller / TMA / MMA issuer
 constexpr int NTHR = 160;
 constexpr size_t C4_HDR = 1024;   // scratch: grid barrier counter

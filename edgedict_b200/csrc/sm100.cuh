@@ -110,6 +110,14 @@ __device__ __forceinline__ void cluster_sync_all() {
 // generic-proxy writes (st.global / st.shared) -> async-proxy reads (TMA, tcgen05.mma operand fetch)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
+// bulk copy shared::cta -> shared::cluster (DSMEM) by the copy engine, completing (bytes) on an mbarrier of the destination
+__device__ __forceinline__ void bulk_s2c(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t mbar_cluster) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst_cluster), "r"(src_cta), "r"(bytes), "r"(mbar_cluster) : "memory");
+}
+// generic-proxy writes to shared memory -> async-proxy reads of it (bulk copies, tcgen05.mma operands)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // ---- host side: TMA descriptors -------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,

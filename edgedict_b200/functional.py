@@ -375,6 +375,9 @@ class LSTMStack(torch.autograd.Function):
         P = [params[6 * l:6 * l + 6] for l in range(L)]
         ck = [_Chunks(B, lens) for lens in plan]
         dev = dout.device
+        main = torch.cuda.current_stream(dev)
+        side = _side_streams(dev)[0]
+        side.wait_stream(main)
         g = ck[L].scatter(_c(dout))                           # d xs[L], chunk-major
         grads = [None] * (6 * L)
         for l in range(L - 1, -1, -1):
@@ -407,16 +410,32 @@ class LSTMStack(torch.autograd.Function):
                         hp[:, 0] = k.blk(y16[l], c - 1)[:, -1]
                     else:
                         hp[:, 0].zero_()
-            dx = ops.mm_nn(dg16, P[l][0], "bf16", dy16=dg16) if (l > 0 or ctx.needs_input_grad[0]) else None
-            grads[6 * l + 0] = ops.mm_tn(dg16, x16[l], "bf16", dy16=dg16, x16=x16[l])
-            grads[6 * l + 1] = ops.mm_tn(dg16, hprev, "bf16", dy16=dg16, x16=hprev)
-            db = ops.colsum(dg16)
-            grads[6 * l + 2], grads[6 * l + 3] = db, db.clone()
-            grads[6 * l + 4], grads[6 * l + 5] = dgamma, dbeta
+            # critical path to the next layer: d x = dG W_ih (+ dz: the LayerNorm residual branch, accumulated by the
+            # GEMM's epilogue straight into dz)
+            wih16 = ops.cast_bf16(_c(P[l][0]))
+            M, I_l = dg16.shape[0], P[l][0].shape[1]
             if l > 0:
-                g = dx.add_(dz)                               # through the LSTM input + the LayerNorm residual
+                g = ops.gemm_bf16(dg16, 0, wih16, 1, M, I_l, 4 * H, out=dz, accumulate=True, tag="gemm_bf16_nn")
+            elif ctx.needs_input_grad[0]:
+                g = ops.gemm_bf16(dg16, 0, wih16, 1, M, I_l, 4 * H, tag="gemm_bf16_nn")
             else:
-                g = dx
+                g = None
+            # off the critical path: the weight / bias gradients of this layer run on a side stream under the BPTT
+            # recurrence of the next layer (which leaves 20 SMs idle and the tensor pipe nearly so)
+            ready = torch.cuda.Event()
+            ready.record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(ready)
+                grads[6 * l + 0] = ops.mm_tn(dg16, x16[l], "bf16", dy16=dg16, x16=x16[l])
+                grads[6 * l + 1] = ops.mm_tn(dg16, hprev, "bf16", dy16=dg16, x16=hprev)
+                db = ops.colsum(dg16)
+                grads[6 * l + 2], grads[6 * l + 3] = db, db.clone()
+                for t_ in (dg16, hprev):
+                    t_.record_stream(side)
+                for t_ in grads[6 * l:6 * l + 4]:
+                    t_.record_stream(main)
+            grads[6 * l + 4], grads[6 * l + 5] = dgamma, dbeta
+        main.wait_stream(side)
         dxin = ck[0].gather(g) if g is not None else None
         return (dxin, None, *grads)
 

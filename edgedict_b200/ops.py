@@ -556,3 +556,11 @@ def logmel_frontend(x, basis, fbT, n_fft, hop, n_mels, n_stack, preemph, take_lo
     check(lib().eb_fe_log_stack(_p(mel), _p(out), B, R, Fs, seq_len, n_mels, n_stack, T, int(take_log), _s()),
           "eb_fe_log_stack")
     return out
+
+
+def fe_mask(x, spans, axis, fill=0.0):
+    """SpecAugment masking in place: x [B, D1, D2] fp32, spans int32 [B, nmask, 2] along axis 1 or 2."""
+    _need(x, f32, "x")
+    B, D1, D2 = x.shape
+    check(lib().eb_fe_mask(_p(x), _p(spans), B, D1, D2, spans.shape[1], axis, float(fill), _s()), "eb_fe_mask")
+    return x

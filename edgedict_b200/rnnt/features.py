@@ -124,11 +124,55 @@ class LogMelFrontend(nn.Module):
         return self.fbank._features(x, self.downsample, self.pad_to_divisible)
 
 
+class _SpanMasking(nn.Module):
+    """SpecAugment masking of rnnt/transforms.py:53-147 on the [B, C, T] feature layout.  The spans are drawn on the
+    host with python's `random` in exactly the reference's order (per utterance, per mask: start = randrange(dim),
+    end = start + randrange(max_width)), so `random.seed(s)` reproduces the reference's masks; they are applied by
+    one kernel (eb_fe_mask) instead of a boolean mask tensor + masked_fill."""
+    axis = 2
+
+    def __init__(self, max_width, num_masks, use_mean=False):
+        super().__init__()
+        self.max_width, self.num_masks, self.use_mean = max_width, num_masks, use_mean
+
+    @torch.no_grad()
+    def forward(self, x):
+        import random
+        fill = float(x.mean()) if self.use_mean else 0.0
+        dim = x.shape[self.axis]
+        spans = []
+        for _ in range(x.shape[0]):
+            row = []
+            for _ in range(self.num_masks):
+                start = random.randrange(0, dim)
+                row.append((start, start + random.randrange(0, self.max_width)))
+            spans.append(row)
+        if self.num_masks == 0:
+            return x
+        sp = torch.tensor(spans, dtype=torch.int32).to(x.device, non_blocking=True)
+        out = x.contiguous().clone()                      # masked_fill is out of place in the reference
+        return ops.fe_mask(out, sp, self.axis, fill)
+
+    def __repr__(self):
+        return "%s(max_width=%d,num_masks=%d,use_mean=%s)" % (self.__class__.__name__, self.max_width, self.num_masks,
+                                                               self.use_mean)
+
+
+class TimeMasking(_SpanMasking):
+    """rnnt/transforms.py:102-147: `mask[i, :, start:end] = 1` on the last (time) axis."""
+    axis = 2
+
+
+class FrequencyMasking(_SpanMasking):
+    """rnnt/transforms.py:53-99: `mask[i, start:end, :] = 1` on the channel axis."""
+    axis = 1
+
+
 def build_transform(feature_type, feature_size, n_fft=512, win_length=400, hop_length=200, delta=False, cmvn=False,
                     downsample=1, T_mask=0, T_num_mask=0, F_mask=0, F_num_mask=0, pad_to_divisible=True):
     """rnnt/transforms.py:165-203 for feature_type='logfbank' without deltas (every BASELINE flagfile); returns
-    (transform_train, transform_test, input_size) producing the reference's [B, C, T] layout.  SpecAugment masking
-    of the train transform is left to the caller's data pipeline (random, host-side in the reference)."""
+    (transform_train, transform_test, input_size) producing the reference's [B, C, T] layout; the train transform
+    appends the SpecAugment time / frequency masks exactly where the reference does (transforms.py:195-199)."""
     if feature_type != "logfbank" or delta:
         raise NotImplementedError("edgedict_b200 front end implements feature_type='logfbank', delta=False")
     mods = [FilterbankFeatures(n_filt=feature_size, n_fft=n_fft, win_length=win_length, hop_length=hop_length)]
@@ -137,4 +181,10 @@ def build_transform(feature_type, feature_size, n_fft=512, win_length=400, hop_l
         mods.append(Downsample(downsample, pad_to_divisible))
         input_size *= downsample
     test = nn.Sequential(*mods)
-    return test, test, input_size
+    train_mods = list(mods)
+    if T_mask > 0 and T_num_mask > 0:
+        train_mods.append(TimeMasking(T_mask, T_num_mask))
+    if F_mask > 0 and F_num_mask > 0:
+        train_mods.append(FrequencyMasking(F_mask, F_num_mask))
+    train = nn.Sequential(*train_mods) if len(train_mods) > len(mods) else test
+    return train, test, input_size

@@ -22,6 +22,15 @@ from .. import ops
 from .tokenizer import NUL, BOS, PAD
 
 _DEFAULT_PRECISION = os.environ.get("EDGEDICT_PRECISION", "fp32")
+_PREDICTOR_STREAM = os.environ.get("EDGEDICT_PREDICTOR_STREAM", "1") != "0"
+_pred_streams = {}
+
+
+def _predictor_stream(device):
+    s = _pred_streams.get(device)
+    if s is None:
+        s = _pred_streams[device] = torch.cuda.Stream(device)
+    return s
 
 
 def _precision(module):
@@ -115,9 +124,51 @@ class ResLayerNormLSTM(nn.Module):
         return xs, (torch.stack(out_h, 0), torch.stack(out_c, 0))
 
 
+class ResLayerNormGRU(nn.Module):
+    """rnnt/models.py:77-116, the GRU encoder variant (`module_type='GRU'`, only cli/lightning.py:63 selects it).
+    SURVEY 8(a) a22: kept as a TORCH FALLBACK -- nn.GRU / nn.LayerNorm run through ATen (cuDNN on a GPU), not through
+    this library's kernels; same constructor, ``state_dict`` keys (`lstms.{i}`, `projs.{i}.0`) and return value
+    (xs, hs [L, B, H]) as the reference, so a GRU checkpoint loads and decodes."""
+
+    def __init__(self, input_size, hidden_size, num_layers, dropout=0, time_reductions=[1], reduction_factor=2):
+        super().__init__()
+        self.hidden_size = hidden_size
+        self.lstms = nn.ModuleList()
+        self.projs = nn.ModuleList()
+        self.time_reductions = set(time_reductions)
+        for i in range(num_layers):
+            self.lstms.append(nn.GRU(input_size, hidden_size, 1, batch_first=True))
+            proj = [nn.LayerNorm(hidden_size)]
+            if i in self.time_reductions:
+                proj.append(TimeReduction(reduction_factor))
+            if dropout > 0:
+                proj.append(nn.Dropout(dropout))
+            input_size = hidden_size
+            self.projs.append(nn.Sequential(*proj))
+
+    @staticmethod
+    def _time_reduce(x, factor=2):
+        B, T, H = x.shape
+        pad = (factor - T % factor) % factor
+        if pad:
+            x = nn.functional.pad(x, [0, 0, 0, pad])
+        return x.reshape(B, -1, factor, H).mean(2)
+
+    def forward(self, xs, hiddens=None):
+        hs = xs.new_zeros(len(self.lstms), xs.shape[0], self.hidden_size) if hiddens is None else hiddens
+        new_hs = []
+        for i, (gru, proj) in enumerate(zip(self.lstms, self.projs)):
+            ys, h = gru(xs, hs[i, None].contiguous())
+            xs = ys if i == 0 else xs + ys
+            for m in proj:                                   # torch modules, except the parameter-free reduction
+                xs = self._time_reduce(xs, m.reduction_factor) if isinstance(m, TimeReduction) else m(xs)
+            new_hs.append(h)
+        return xs, torch.cat(new_hs, dim=0)
+
+
 class Encoder(nn.Module):
-    """rnnt/models.py:119-136.  ``module`` defaults to the LSTM stack (the reference default is the
-    GRU variant, which no BASELINE config uses and which this engine does not implement)."""
+    """rnnt/models.py:119-136.  ``module`` defaults to the LSTM stack (the reference's default argument is the GRU
+    variant, but every caller that matters passes the LSTM one; ResLayerNormGRU above is the torch fallback)."""
 
     def __init__(self, input_size, hidden_size, num_layers, dropout, proj_size,
                  module=ResLayerNormLSTM, time_reductions=[1], has_proj=True):
@@ -199,12 +250,11 @@ class Transducer(nn.Module):
         self.blank = blank
         if module_type not in ['GRU', 'LSTM']:
             raise ValueError('Unsupported module type')
-        if module_type == 'GRU':
-            raise NotImplementedError("edgedict_b200 builds the LSTM encoder (module_type='LSTM'); the GRU "
-                                      "variant (rnnt/models.py:77-116) is outside the B200 hot path")
+        # rnnt/models.py:196-205: the GRU variant runs as a torch fallback, the LSTM one on this engine
         self.encoder = Encoder(input_size=input_size, hidden_size=enc_hidden_size, num_layers=enc_layers,
                                dropout=enc_dropout, proj_size=enc_proj_size,
-                               time_reductions=enc_time_reductions, module=ResLayerNormLSTM)
+                               time_reductions=enc_time_reductions,
+                               module=ResLayerNormGRU if module_type == 'GRU' else ResLayerNormLSTM)
         self.decoder = Decoder(vocab_embed_size=vocab_embed_size, vocab_size=vocab_size,
                                hidden_size=dec_hidden_size, num_layers=dec_layers, dropout=dec_dropout,
                                proj_size=dec_proj_size)
@@ -225,8 +275,21 @@ class Transducer(nn.Module):
     def forward(self, xs, ys, xlen, ylen):
         xs = xs[:, :int(xlen.max())].contiguous()
         ys = ys[:, :int(ylen.max())].contiguous()
-        h_enc, _ = self.encoder(xs)
-        h_dec, _ = self.decoder(ys)
+        if xs.is_cuda and _PREDICTOR_STREAM:
+            # The prediction network (2 x 129 recurrent steps) is independent of the encoder until the joint: it runs on
+            # a side stream under the encoder's recurrence (its kernels use 32 of the 148 SMs at H_d = 256); autograd
+            # replays each node's backward on the stream of its forward, so the backward passes overlap the same way.
+            main = torch.cuda.current_stream(xs.device)
+            side = _predictor_stream(xs.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                h_dec, _ = self.decoder(ys)
+            h_enc, _ = self.encoder(xs)
+            main.wait_stream(side)
+            h_dec.record_stream(main)
+        else:
+            h_enc, _ = self.encoder(xs)
+            h_dec, _ = self.decoder(ys)
         if not self.output_loss:
             return self.joint(h_enc, h_dec)
         xl = scale_length(h_enc.shape[1], xlen).to(device=h_enc.device)
@@ -256,6 +319,61 @@ class Transducer(nn.Module):
         ids = ids.cpu().numpy()
         out = [ids[i, :int(n)].astype("int64") for i, n in enumerate(xlen)]
         return out, -logp.clone()
+
+
+    @torch.no_grad()
+    def beam_search(self, xs, xlen=None, W=4, merge=True):
+        """beam decode.  The reference has no beam search in rnnt/ (north_star mentions one); its
+        legacy v0 stack holds a batch-1 Graves-style search (models.py:121-202, with no-op `sorted(...)` calls and a
+        removed `volatile=` API).  This is a time-synchronous beam under the SAME emission constraint as
+        `greedy_decode` (at most one symbol per encoder frame, rnnt/models.py:243-269): per frame every hypothesis is
+        scored against the whole vocabulary in one joint call, the W best continuations survive (hypotheses that
+        reach the same token sequence are merged by log-add when `merge`), and only the survivors that emitted a
+        non-blank take a predictor step (one batched call).  W = 1 reproduces `greedy_decode` token for token.
+        xs [B,T,F] -> (list of non-blank id lists, -log p [B]); utterances are searched one at a time like the
+        reference's beam."""
+        h_enc_all, _ = self.encoder(xs)
+        B, Tn = h_enc_all.shape[0], h_enc_all.shape[1]
+        dev = h_enc_all.device
+        outs, nlps = [], []
+        for b in range(B):
+            frames = Tn if xlen is None else min(Tn, int(scale_length(Tn, xlen)[b]))
+            dec_x, (dh, dc) = self.decoder(torch.zeros(1, 0, dtype=torch.long, device=dev))     # BOS prime
+            dec_x = dec_x[:, 0]                                                                   # [n, D]
+            seqs, logp = [[]], torch.zeros(1, device=dev)
+            for t in range(frames):
+                n = dec_x.shape[0]
+                he = h_enc_all[b, t][None].expand(n, -1).contiguous()
+                logits = self.joint(he, dec_x.contiguous())                                      # [n, V]
+                lp = torch.log_softmax(logits.float(), 1) + logp[:, None]                        # [n, V]
+                V = lp.shape[1]
+                top, idx = lp.reshape(-1).topk(min(W, n * V))                                   # ties: lowest index first
+                par, tok = (idx // V).tolist(), (idx % V).tolist()
+                new_seqs = [seqs[q] + ([k] if k != self.blank else []) for q, k in zip(par, tok)]
+                keep, merged_lp, seen = [], [], {}
+                for i, sq in enumerate(new_seqs):
+                    key = tuple(sq)
+                    if merge and key in seen:
+                        j = seen[key]
+                        merged_lp[j] = torch.logaddexp(merged_lp[j], top[i])
+                        continue
+                    seen[key] = len(keep)
+                    keep.append(i)
+                    merged_lp.append(top[i])
+                par_t = torch.tensor([par[i] for i in keep], device=dev)
+                tok_t = torch.tensor([tok[i] for i in keep], device=dev)
+                seqs = [new_seqs[i] for i in keep]
+                logp = torch.stack(merged_lp)
+                dec_x, dh, dc = dec_x[par_t], dh[:, par_t], dc[:, par_t]
+                nb = (tok_t != self.blank).nonzero()[:, 0]
+                if nb.numel():
+                    nx, (nh, nc) = self.decoder(tok_t[nb][:, None], (dh[:, nb].contiguous(), dc[:, nb].contiguous()))
+                    dec_x, dh, dc = dec_x.clone(), dh.clone(), dc.clone()
+                    dec_x[nb], dh[:, nb], dc[:, nb] = nx[:, 0], nh, nc
+            best = int(logp.argmax())
+            outs.append(seqs[best])
+            nlps.append(-logp[best])
+        return outs, torch.stack(nlps)
 
 
 def _i32(t):

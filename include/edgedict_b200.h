@@ -196,6 +196,9 @@ int eb_fe_preemph_pad(const float* x, float* xp, int B, int L, long Lp, int pad,
 int eb_fe_power(const float* spec, float* power, long rows, int nbins, void* stream);
 int eb_fe_log_stack(const float* mel, float* out, int B, int rows_per_utt, int n_frames, int seq_len,
                     int n_mels, int n_stack, int t_out, int take_log, void* stream);
+/* SpecAugment masks (rnnt/transforms.py:53-147) in place on x [B, D1, D2]: spans int32 [B, nmask, 2] = [start, end)
+ * along axis 1 (frequency) or 2 (time); masked elements := fill. */
+int eb_fe_mask(float* x, const int* spans, int B, int D1, int D2, int nmask, int axis, float fill, void* stream);
 
 #ifdef __cplusplus
 }

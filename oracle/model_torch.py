@@ -185,6 +185,75 @@ def greedy_decode(sd, xs, xlen, blank=NUL, time_reductions=(1,), fast=False):
     return [s[:int(n)].numpy() for s, n in zip(seq, xlen)], -torch.stack(lps, 1).sum(1)
 
 
+@torch.no_grad()
+def beam_search(sd, xs, xlen=None, W=4, blank=NUL, merge=True, time_reductions=(1,)):
+    """Restatement of edgedict_b200's time-synchronous beam (Transducer.beam_search; SURVEY 8(f) N4 -- the reference
+    holds no beam search in rnnt/, so the pin is W = 1 == greedy_decode plus this independent CPU restatement)."""
+    h_enc_all, _ = encoder(sd, xs, None, time_reductions)
+    outs, nlps = [], []
+    for b in range(xs.shape[0]):
+        Tn = h_enc_all.shape[1]
+        frames = Tn if xlen is None else min(Tn, int(scale_length(Tn, xlen)[b]))
+        dec_x, (dh, dc) = decoder(sd, torch.zeros(1, 0, dtype=torch.long), None)
+        hyps = [dict(seq=[], lp=torch.zeros(()), x=dec_x[0, 0], h=dh[:, 0], c=dc[:, 0])]
+        for t in range(frames):
+            cand = []
+            for qi, hy in enumerate(hyps):
+                lp = F.log_softmax(joint(sd, h_enc_all[b, t][None], hy["x"][None])[0], 0) + hy["lp"]
+                cand += [(float(lp[k]), qi, k, lp[k]) for k in range(lp.shape[0])]
+            cand.sort(key=lambda c: (-c[0], c[1], c[2]))
+            new, seen = [], {}
+            for _, qi, k, lpk in cand[:W]:
+                hy = hyps[qi]
+                seq = hy["seq"] + ([k] if k != blank else [])
+                key = tuple(seq)
+                if merge and key in seen:
+                    seen[key]["lp"] = torch.logaddexp(seen[key]["lp"], lpk)
+                    continue
+                nh = dict(seq=seq, lp=lpk, x=hy["x"], h=hy["h"], c=hy["c"])
+                if k != blank:
+                    nx, (h2, c2) = decoder(sd, torch.full((1, 1), k), (hy["h"][:, None], hy["c"][:, None]))
+                    nh.update(x=nx[0, 0], h=h2[:, 0], c=c2[:, 0])
+                seen[key] = nh
+                new.append(nh)
+            hyps = new
+        best = max(hyps, key=lambda h: float(h["lp"]))
+        outs.append(best["seq"])
+        nlps.append(-best["lp"])
+    return outs, torch.stack(nlps)
+
+
+def encoder_gru(sd, xs, hiddens=None, time_reductions=(1,), pre="encoder."):
+    """rnnt/models.py:77-116 + :131-136 (Encoder with ResLayerNormGRU): explicit GRU cell loop, gate order r|z|n."""
+    L = _n(sd, pre + "lstm.lstms.%d.weight_ih_l0")
+    H = sd[pre + "lstm.lstms.0.weight_hh_l0"].shape[1]
+    B = xs.shape[0]
+    hs = xs.new_zeros(L, B, H) if hiddens is None else hiddens
+    x = F.layer_norm(xs, (xs.shape[-1],), sd[pre + "norm.weight"], sd[pre + "norm.bias"], 1e-5)
+    nh = []
+    for i in range(L):
+        p = pre + "lstm.lstms.%d." % i
+        w_ih, w_hh, b_ih, b_hh = (sd[p + k] for k in ("weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0"))
+        h, ys = hs[i], []
+        for t in range(x.shape[1]):
+            gi, gh = x[:, t] @ w_ih.t() + b_ih, h @ w_hh.t() + b_hh
+            r = torch.sigmoid(gi[:, :H] + gh[:, :H])
+            z = torch.sigmoid(gi[:, H:2 * H] + gh[:, H:2 * H])
+            n = torch.tanh(gi[:, 2 * H:] + r * gh[:, 2 * H:])
+            h = (1 - z) * n + z * h
+            ys.append(h)
+        y = torch.stack(ys, 1)
+        x = y if i == 0 else x + y
+        q = pre + "lstm.projs.%d.0." % i
+        x = F.layer_norm(x, (H,), sd[q + "weight"], sd[q + "bias"], 1e-5)
+        if i in time_reductions:
+            x = time_reduction(x)
+        nh.append(h)
+    if (pre + "proj.weight") in sd:
+        x = F.linear(x, sd[pre + "proj.weight"], sd[pre + "proj.bias"])
+    return x, torch.stack(nh)
+
+
 class StreamState:
     def __init__(self, sd, fast=False):
         w = sd["decoder.embed.weight"]

@@ -122,3 +122,51 @@ def test_stream_state_survives_chunk_length_change_and_rehomed_weights():
         ids = eng.step(c.cuda())[0].tolist()
         got.append([t for t in ids if t != 0])
     assert got == want
+
+
+def test_e6d2_large_64_streams_token_for_token():
+    """BASELINE configs[3] shape: E6D2_LARGE (H=1024 x 6, predictor 2 x 512, joint 640, V=1024), 64 concurrent streams,
+    chunks of 2 log-mel frames: every stream, every chunk, token for token against the reference loop restated
+    on the CPU in fp32 (oracle encoder batched over the streams, rnnt/stream.py:97-120 per stream).  The decode
+    kernel's matrix products are 3xTF32 split products on the tensor cores (fp32-accurate)."""
+    from edgedict_b200.rnnt.models import Transducer
+    from edgedict_b200.stream_engine import StreamEngine
+    from oracle import model_torch as mt
+    cfg = dict(vocab_embed_size=64, vocab_size=1024, input_size=240, enc_hidden_size=1024, enc_layers=6, enc_dropout=0.0,
+               enc_proj_size=640, dec_hidden_size=512, dec_layers=2, dec_dropout=0.1, dec_proj_size=640, joint_size=640)
+    S, CHUNKS = 64, 24
+    torch.manual_seed(10)
+    model = Transducer(output_loss=False, **cfg).eval()
+    with torch.no_grad():
+        for p in model.parameters():
+            p.mul_(2.0)                       # random-init weights emit only blanks; scale up so symbols appear
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model.cuda()
+    g = torch.Generator().manual_seed(0)
+    chunks = torch.randn(CHUNKS, S, 2, 240, generator=g)
+    eng = StreamEngine(model, S, 2)
+    got = np.stack([eng.step(c.cuda()).cpu().numpy().copy() for c in chunks])[:, :, 0]          # [chunks, S]
+    # CPU restatement, batched over the streams where the reference is per-stream-independent
+    with torch.no_grad():
+        L, H = 6, 1024
+        eh, ec = torch.zeros(L, S, H), torch.zeros(L, S, H)
+        one = mt.StreamState(sd)
+        dec_x = one.dec_x.repeat(S, 1, 1)
+        dec_h, dec_c = one.dec_h.repeat(1, S, 1), one.dec_c.repeat(1, S, 1)
+        want = np.zeros((CHUNKS, S), dtype=np.int64)
+        for ci in range(CHUNKS):
+            enc, (eh, ec) = mt.encoder(sd, chunks[ci], (eh, ec), fast=True)
+            assert enc.shape[1] == 1
+            prob = mt.joint(sd, enc[:, 0], dec_x[:, 0])
+            pred = prob.argmax(-1)
+            unk = pred == 3
+            if unk.any():
+                prob[unk, 3] = 0
+                pred = prob.argmax(-1)
+            want[ci] = pred.numpy()
+            nb = pred != 0
+            if nb.any():
+                nx, (nh, nc) = mt.decoder(sd, pred[nb][:, None], (dec_h[:, nb], dec_c[:, nb]), fast=True)
+                dec_x[nb], dec_h[:, nb], dec_c[:, nb] = nx, nh, nc
+    assert (want != 0).sum() > 50                              # the test really exercises the predictor
+    assert (got == want).all(), "streams differ at %s" % (np.argwhere(got != want)[:5].tolist(),)
