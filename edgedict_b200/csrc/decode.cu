@@ -88,16 +88,38 @@ __device__ __forceinline__ void tile_mma(float (&acc)[4][4][4], AF arow, BF brow
                                          bool bvec, int& step_ctr) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
     const int nmt = (nrows + 15) >> 4;
-    for (int k0 = 0; k0 < K; k0 += 16, ++step_ctr) {
-        if ((step_ctr & (NWARP - 1)) != w) continue;
-        const int k = k0 + 4 * t;
-        float4 bv[4];
+    const int nsteps = (K + 15) >> 4;
+    // this warp's steps of the segment: first, then every NWARP-th
+    int i = (w - (step_ctr & (NWARP - 1)) + NWARP) & (NWARP - 1);
+    step_ctr += nsteps;
+    if (i >= nsteps) return;
+    // operand rows are fixed across the steps: resolve the pointers once
+    const float* bp[4];
+    const float* ap[4][2];
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
-            const int n = nt * 8 + g;
-            bv[nt] = (n < ncols) ? load_k4<false>(brow(n), k, K, bvec) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int nt = 0; nt < 4; ++nt) bp[nt] = (nt * 8 + g < ncols) ? brow(nt * 8 + g) : nullptr;
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+        ap[mt][0] = (mt < nmt && mt * 16 + g < nrows) ? arow(mt * 16 + g) : nullptr;
+        ap[mt][1] = (mt < nmt && mt * 16 + g + 8 < nrows) ? arow(mt * 16 + g + 8) : nullptr;
+    }
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 bv[4], av[4][2];
+    auto fetch = [&](int step) {
+        const int k = step * 16 + 4 * t;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) bv[nt] = bp[nt] ? load_k4<false>(bp[nt], k, K, bvec) : zero4;
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+            av[mt][0] = ap[mt][0] ? load_k4<true>(ap[mt][0], k, K, avec) : zero4;
+            av[mt][1] = ap[mt][1] ? load_k4<true>(ap[mt][1], k, K, avec) : zero4;
         }
-        uint32_t bh[4][4], bl[4][4];
+    };
+    fetch(i);
+    for (; i < nsteps; i += NWARP) {
+        // split the operands of this step, then issue the loads of the next one before the MMAs (weights stream from
+        // HBM: one step of latency is hidden behind 96 MMAs)
+        uint32_t bh[4][4], bl[4][4], ah[4][2][4], al[4][2][4];
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
             split_tf32(bv[nt].x, bh[nt][0], bl[nt][0]);
@@ -107,22 +129,23 @@ __device__ __forceinline__ void tile_mma(float (&acc)[4][4][4], AF arow, BF brow
         }
 #pragma unroll
         for (int mt = 0; mt < 4; ++mt) {
+            const float4 a0 = av[mt][0], a1 = av[mt][1];
+            split_tf32(a0.x, ah[mt][0][0], al[mt][0][0]); split_tf32(a1.x, ah[mt][0][1], al[mt][0][1]);
+            split_tf32(a0.y, ah[mt][0][2], al[mt][0][2]); split_tf32(a1.y, ah[mt][0][3], al[mt][0][3]);
+            split_tf32(a0.z, ah[mt][1][0], al[mt][1][0]); split_tf32(a1.z, ah[mt][1][1], al[mt][1][1]);
+            split_tf32(a0.w, ah[mt][1][2], al[mt][1][2]); split_tf32(a1.w, ah[mt][1][3], al[mt][1][3]);
+        }
+        if (i + NWARP < nsteps) fetch(i + NWARP);
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
             if (mt < nmt) {
-                const int r0 = mt * 16 + g, r1 = r0 + 8;
-                const float4 a0 = (r0 < nrows) ? load_k4<true>(arow(r0), k, K, avec) : make_float4(0.f, 0.f, 0.f, 0.f);
-                const float4 a1 = (r1 < nrows) ? load_k4<true>(arow(r1), k, K, avec) : make_float4(0.f, 0.f, 0.f, 0.f);
-                uint32_t ah[2][4], al[2][4];
-                split_tf32(a0.x, ah[0][0], al[0][0]); split_tf32(a1.x, ah[0][1], al[0][1]);
-                split_tf32(a0.y, ah[0][2], al[0][2]); split_tf32(a1.y, ah[0][3], al[0][3]);
-                split_tf32(a0.z, ah[1][0], al[1][0]); split_tf32(a1.z, ah[1][1], al[1][1]);
-                split_tf32(a0.w, ah[1][2], al[1][2]); split_tf32(a1.w, ah[1][3], al[1][3]);
 #pragma unroll
                 for (int e = 0; e < 2; ++e)
 #pragma unroll
                     for (int nt = 0; nt < 4; ++nt) {
-                        mma_tf32(acc[mt][nt], al[e], bh[nt][2 * e], bh[nt][2 * e + 1]);
-                        mma_tf32(acc[mt][nt], ah[e], bl[nt][2 * e], bl[nt][2 * e + 1]);
-                        mma_tf32(acc[mt][nt], ah[e], bh[nt][2 * e], bh[nt][2 * e + 1]);
+                        mma_tf32(acc[mt][nt], al[mt][e], bh[nt][2 * e], bh[nt][2 * e + 1]);
+                        mma_tf32(acc[mt][nt], ah[mt][e], bl[nt][2 * e], bl[nt][2 * e + 1]);
+                        mma_tf32(acc[mt][nt], ah[mt][e], bh[nt][2 * e], bh[nt][2 * e + 1]);
                     }
             }
         }

@@ -47,9 +47,21 @@ constexpr int NTHR = 160;
 constexpr size_t C4_HDR = 1024;   // scratch: grid barrier counter
 
 // debug stamps: slot s of step `step` <- clock64() (CTA 0 only; the pointer is null in production)
+__device__ __forceinline__ long long gtimer() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// trace_steps > 0: clock64 stamps of CTA 0, [step][16].  trace_steps < 0: globaltimer stamps of EVERY CTA for the first
+// -trace_steps steps, [step][cta][16] (skew between CTAs).
 #define C4_STAMP(step, s)                                                                          \
     do {                                                                                           \
-        if (p.trace && blockIdx.x == 0 && (step) < p.trace_steps) p.trace[(size_t)(step) * 16 + (s)] = clock64(); \
+        if (p.trace) {                                                                             \
+            if (p.trace_steps > 0) {                                                               \
+                if (blockIdx.x == 0 && (step) < p.trace_steps) p.trace[(size_t)(step) * 16 + (s)] = clock64(); \
+            } else if ((step) < -p.trace_steps)                                                    \
+                p.trace[((size_t)(step) * gridDim.x + blockIdx.x) * 16 + (s)] = gtimer();          \
+        }                                                                                          \
     } while (0)
 long long* g_trace = nullptr;
 int g_trace_steps = 0;
@@ -162,7 +174,13 @@ __global__ void __launch_bounds__(NGT, 2) lstm_c4_fwd_kernel(C4FwdP p) {
         if (own && p.hprev16) *reinterpret_cast<uint32_t*>(p.hprev16 + (size_t)b * T * H + j) = hp;
     }
     __syncthreads();
-    if (tid == 0) { __threadfence(); atomicAdd(p.bar, 1u); }
+    // Grid barrier per K SLICE: the CTA of rank r only consumes the h units of slice r, produced by the NC/4 CTAs
+    // [r*NC/4, (r+1)*NC/4): it waits for those arrivals alone (counter r, 128 bytes apart).  Every cluster consumes
+    // all four slices, so no CTA can run a step ahead of any producer and the double-buffered exchange stays safe.
+    const unsigned nprod = ncta >> 2;
+    unsigned* const my_ctr = p.bar + (cta / (int)nprod) * 32;
+    const unsigned* const wait_ctr = p.bar + rank * 32;
+    if (tid == 0) { __threadfence(); atomicAdd(my_ctr, 1u); }
     const float* xgp = p.xg + (size_t)b * T * 4 * H + j;
     float2 xr[4];
 #pragma unroll
@@ -183,7 +201,7 @@ __global__ void __launch_bounds__(NGT, 2) lstm_c4_fwd_kernel(C4FwdP p) {
     for (int t = 0; t < T; ++t) {
         const uint32_t ph = (uint32_t)(t & 1);
         // ---- grid barrier: every CTA has published h_{t-1}; one poller, then the block
-        if (tid == 0) spin_wait_ge(p.bar, (unsigned)(t + 1) * ncta);
+        if (tid == 0) spin_wait_ge(wait_ctr, (unsigned)(t + 1) * nprod);   // (a back-off between polls changes nothing: measured)
         __syncthreads();
         if (tid == 0) C4_STAMP(t, 0);
         // ---- A. pull this CTA's K slice of h_{t-1} (L2 -> registers -> swizzled shared tile)
@@ -267,7 +285,7 @@ __global__ void __launch_bounds__(NGT, 2) lstm_c4_fwd_kernel(C4FwdP p) {
             C4_STAMP(t, 7);
             __threadfence();
             C4_STAMP(t, 8);
-            atomicAdd(p.bar, 1u);
+            atomicAdd(my_ctr, 1u);
         }
         // everything below overlaps the other CTAs' progress towards the barrier
         if (own) {

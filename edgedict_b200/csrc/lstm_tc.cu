@@ -362,6 +362,11 @@ __global__ void __launch_bounds__(NW * 32, 1) lstm_tc_bwd_kernel(BwdP p) {
     float dh = (own && p.dhT) ? p.dhT[(long)bb * H + j] : 0.f;
     float dc = (own && p.dcT) ? p.dcT[(long)bb * H + j] : 0.f;
     unsigned epoch = 0;
+    // grid barrier per K slice (see lstm_c4.cu): this CTA consumes slice rs of dG_t, produced by the ncta/CS CTAs that
+    // own the units [rs*H/CS, (rs+1)*H/CS); it arrives on the counter of the slice its own units belong to
+    const unsigned nprod = ncta / CS;
+    unsigned* const my_ctr = p.bar + ((js * JS + rs * UPC) / (H / CS)) * 32;
+    const unsigned* const wait_ctr = p.bar + rs * 32;
     const uint32_t rbar = smem_u32(rbar_p);
     if (CLUSTER) {
         if (tid == 0) {
@@ -421,7 +426,7 @@ __global__ void __launch_bounds__(NW * 32, 1) lstm_tc_bwd_kernel(BwdP p) {
         __syncthreads();
         ++epoch;
         TC_STAMP(T - 1 - t, 1);
-        if (tid == 0) { __threadfence(); atomicAdd(p.bar, 1u); }
+        if (tid == 0) { __threadfence(); atomicAdd(my_ctr, 1u); }
         TC_STAMP(T - 1 - t, 2);
         if (tid < NB * 4) {   // off the critical path: dG_t in the standard gate-major layout, 16-byte stores
             const int b = tid >> 2, c = tid & 3;
@@ -430,7 +435,7 @@ __global__ void __launch_bounds__(NW * 32, 1) lstm_tc_bwd_kernel(BwdP p) {
                 *reinterpret_cast<const uint4*>(sg + (b * 4 + c) * UPC);
         }
         EB_PREFETCH(t - 1)                                   // overlaps the wait
-        if (tid == 0) spin_wait_ge(p.bar, epoch * ncta);     // one poller per CTA (see forward kernel)
+        if (tid == 0) spin_wait_ge(wait_ctr, epoch * nprod);  // one poller per CTA (see forward kernel)
         TC_STAMP(T - 1 - t, 3);
         __syncthreads();
         TC_STAMP(T - 1 - t, 4);

@@ -282,6 +282,7 @@ class Transducer(nn.Module):
             main = torch.cuda.current_stream(xs.device)
             side = _predictor_stream(xs.device)
             side.wait_stream(main)
+            ys.record_stream(side)
             with torch.cuda.stream(side):
                 h_dec, _ = self.decoder(ys)
             h_enc, _ = self.encoder(xs)

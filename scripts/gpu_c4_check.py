@@ -142,3 +142,37 @@ if "trace_bwd" in what:
         print("  +%7.0f cyc  %s" % (float((t[:, i] - base).mean()), n))
     per = float((t[1:, 0] - t[:-1, 0]).mean())
     print("  old BPTT step period %.0f cyc = %.2f us at 1.965 GHz" % (per, per / 1965))
+
+
+if "skew" in what:
+    B, T, H = 32, 300, 1024
+    torch.manual_seed(0)
+    xg = torch.randn(B, T, 4 * H, device=dev)
+    w = (torch.randn(4 * H, H, device=dev) / 32).bfloat16()
+    ops.lstm_c4_fwd(xg, w, None, None, True)
+    NS = 200
+    tr = torch.zeros(NS, 128, 16, dtype=torch.int64, device=dev)
+    lib().eb_lstm_c4_set_trace(tr.data_ptr(), -NS)
+    ops.lstm_c4_fwd(xg, w, None, None, True)
+    torch.cuda.synchronize()
+    lib().eb_lstm_c4_set_trace(None, 0)
+    t = tr.cpu().double()[50:NS]                       # [steps, cta, slot]  (ns)
+    # per step: when did each CTA pass the barrier (0), finish the pull (1), get acc (3), pass rbar (5), store h (6), fence done (8)
+    t0 = t[:, :, 0].min(dim=1, keepdim=True).values
+    def col(i):
+        return (t[:, :, i] - t0)
+    import numpy as np
+    names = {0: "barrier passed", 1: "pull + sync", 3: "acc ready", 4: "tiles staged", 5: "rbar passed", 6: "h stored", 8: "fence done"}
+    print("per-CTA time since the FIRST CTA passed the barrier of the step (ns): mean over steps, then min / median / max over CTAs")
+    for i, n in names.items():
+        m = col(i).mean(0).numpy()
+        print("  %-16s min %6.0f  med %6.0f  max %6.0f   slowest CTAs %s" % (n, m.min(), np.median(m), m.max(), np.argsort(-m)[:6].tolist()))
+    per = (t[1:, :, 0] - t[:-1, :, 0]).mean().item()
+    print("  step period %.0f ns" % per)
+    dur = {"pull": (1, 0), "mma": (3, 1), "stage": (4, 3), "dsmem": (5, 4), "gates": (6, 5), "fence": (8, 6)}
+    for n, (a, b) in dur.items():
+        m = (t[:, :, a] - t[:, :, b]).mean(0).numpy()
+        print("  phase %-6s per CTA: min %6.0f med %6.0f max %6.0f ns" % (n, m.min(), np.median(m), m.max()))
+    late = col(8).mean(0).numpy()
+    print("  fence-done lateness by cluster rank:", [round(float(late[r::4].mean())) for r in range(4)])
+    print("  fence-done lateness, CTAs 0..127 in 8 groups of 16:", [round(float(late[i*16:(i+1)*16].mean())) for i in range(8)])

@@ -87,7 +87,8 @@ def test_gru_encoder_variant_torch_fallback():
     sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
     ref, rh = mt.encoder_gru(sd, xs)
     assert out.shape == ref.shape == (2, 6, 40) and hs.shape == (3, 2, 48)
-    assert rel_err(out.cpu(), ref) < 1e-4 and rel_err(hs.cpu(), rh) < 1e-4
+    # torch fallback on a GPU = cuDNN's GRU, which runs its GEMMs in TF32 by default: 1e-3, not fp32 round-off
+    assert rel_err(out.cpu(), ref) < 1e-3 and rel_err(hs.cpu(), rh) < 1e-3
     ys = torch.randint(4, 64, (2, 5), dtype=torch.int32).cuda()
     logits = m(xs.cuda(), ys, torch.tensor([11, 11]), torch.tensor([5, 5]))
     assert logits.shape == (2, 6, 6, 64)
