@@ -433,11 +433,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
 }
 
-// EB_GEMM_MAX_CTAS(n) in the launch flags caps the persistent grid (0 = one CTA per SM): a background GEMM that should
-// stay on the SMs a co-running persistent recurrent kernel leaves free instead of competing with it for L2 bandwidth
-int g_grid_cap = 0;
-inline int grid_cap() { return (g_grid_cap > 0 && g_grid_cap < eb_num_sms()) ? g_grid_cap : eb_num_sms(); }
-
 template <bool A_MN, bool B_MN, int BN_>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, void* C, int c_bf16, const float* bias, int accumulate,
            long M, int N, long K, cudaStream_t st, const void* aux = nullptr) {
@@ -469,7 +464,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, void* C, int c_bf16, co
     }
     if (ksplit > 1 && !accumulate) EB_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, st));
     const long tiles = out_tiles * ksplit;
-    const int grid = (int)(tiles < grid_cap() ? tiles : grid_cap());
+    const int grid = (int)(tiles < eb_num_sms() ? tiles : eb_num_sms());
     // short contraction per tile => the epilogue, not the MMA, paces the tile: use 8 epilogue warps
     static int force_epw = -1;
     if (force_epw < 0) { const char* e = getenv("EDGEDICT_GEMM_EPW"); force_epw = e ? atoi(e) : 0; }
@@ -586,7 +581,6 @@ static int gemm_dispatch(const void* A, int a_mn_major, const void* B, int b_mn_
                          void* stream) {
     if (!A || !B || !C || M <= 0 || N <= 0 || K <= 0) return EB_ERR_INVALID;
     const bool low = (flags & EB_GEMM_CORESIDENT) != 0;
-    g_grid_cap = (flags >> 8) & 0xff;
     if (low && (a_mn_major || b_mn_major)) return EB_ERR_INVALID;
     if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return EB_ERR_INVALID;
     // contiguous dimension must keep row pitches 16-byte aligned

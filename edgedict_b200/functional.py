@@ -184,10 +184,7 @@ class LSTMLayer(torch.autograd.Function):
 # stream while layer l runs chunk c+1: two persistent kernels (compiled for <= 128 registers, ~100 KB of shared
 # memory each) are co-resident on every SM and hide each other's latency.  The per-chunk input GEMM uses the
 # co-resident tile configuration (EB_GEMM_CORESIDENT) so that it fits next to the other layer's recurrent CTA.
-# grid cap of the weight-gradient GEMMs that run under the next layer's BPTT kernel (which holds 128 of the 148 SMs):
-# 0 = full grid (they then share SMs and L2 bandwidth with the recurrence)
-WGRAD_CTAS = int(os.environ.get("EDGEDICT_WGRAD_CTAS", "0"))
-WAVEFRONT_CHUNKS = int(os.environ.get("EDGEDICT_WAVEFRONT_CHUNKS", "4"))     # 0 disables; 4/6/8 measured: 66.5/67.3/67.8 ms
+WAVEFRONT_CHUNKS = int(os.environ.get("EDGEDICT_WAVEFRONT_CHUNKS", "6"))     # 0 disables; 4/6/8 measured: 54.43/54.09/54.40 ms
 _wave_streams = {}
 
 
@@ -429,8 +426,8 @@ class LSTMStack(torch.autograd.Function):
             ready.record(main)
             with torch.cuda.stream(side):
                 side.wait_event(ready)
-                grads[6 * l + 0] = ops.mm_tn(dg16, x16[l], "bf16", dy16=dg16, x16=x16[l], max_ctas=WGRAD_CTAS if l > 0 else 0)
-                grads[6 * l + 1] = ops.mm_tn(dg16, hprev, "bf16", dy16=dg16, x16=hprev, max_ctas=WGRAD_CTAS if l > 0 else 0)
+                grads[6 * l + 0] = ops.mm_tn(dg16, x16[l], "bf16", dy16=dg16, x16=x16[l])
+                grads[6 * l + 1] = ops.mm_tn(dg16, hprev, "bf16", dy16=dg16, x16=hprev)
                 db = ops.colsum(dg16)
                 grads[6 * l + 2], grads[6 * l + 3] = db, db.clone()
                 for t_ in (dg16, hprev):

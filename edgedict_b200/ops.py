@@ -159,14 +159,14 @@ def mm_nn(dy, w, precision="fp32", dy16=None, w16=None, out_bf16=False):
     return gemm_f32(dy, N, 1, w, w.stride(0), w.stride(1), M, K, N)
 
 
-def mm_tn(dy, x, precision="fp32", dy16=None, x16=None, out=None, accumulate=False, max_ctas=0):
-    """dw[N,K] (+)= dy[M,N]^T @ x[M,K]  (contraction over the rows).  max_ctas caps the grid (background GEMM)."""
+def mm_tn(dy, x, precision="fp32", dy16=None, x16=None, out=None, accumulate=False):
+    """dw[N,K] (+)= dy[M,N]^T @ x[M,K]  (contraction over the rows)."""
     M, N = dy.shape
     K = x.shape[1]
     if precision == "bf16":
         dy16 = dy16 if dy16 is not None else (dy if dy.dtype == bf16 else cast_bf16(dy))
         x16 = x16 if x16 is not None else (x if x.dtype == bf16 else cast_bf16(x))
-        return gemm_bf16(dy16, 1, x16, 1, N, K, M, out=out, accumulate=accumulate, flags=(max_ctas & 0xff) << 8)
+        return gemm_bf16(dy16, 1, x16, 1, N, K, M, out=out, accumulate=accumulate)
     _need(dy, f32, "dy")
     _need(x, f32, "x")
     return gemm_f32(dy, 1, N, x, K, 1, N, K, M, out=out, beta=1.0 if accumulate else 0.0)

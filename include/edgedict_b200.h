@@ -60,7 +60,6 @@ int eb_gemm_bf16(const void* A, int a_mn_major, const void* B, int b_mn_major, v
  * configuration that shares an SM with one CTA of a persistent recurrent kernel (eb_lstm_tc_fwd), used by the
  * layer-wavefront schedule of the encoder stack (functional.LSTMStack). */
 #define EB_GEMM_CORESIDENT 1
-#define EB_GEMM_MAX_CTAS(n) (((n) & 0xff) << 8)   /* cap the persistent grid at n CTAs (background GEMMs next to a recurrence) */
 int eb_gemm_bf16_ex(const void* A, int a_mn_major, const void* B, int b_mn_major, void* C, int c_bf16,
                     const float* bias, int accumulate, long M, int N, long K, int flags, void* stream);
 

@@ -208,7 +208,7 @@ def test_layer_wavefront_stack_matches_layer_by_layer(B, T, L, red, H):
         assert (Fn.wavefront_plan(T, [i in red for i in range(L)]) is not None) == (chunks > 0)
         (y * w[:, :y.shape[1]]).sum().backward()
         res.append((y.detach().cpu(), hT.detach().cpu(), cT.detach().cpu(), xi.grad.cpu(), [p.grad.cpu().clone() for p in net.parameters()]))
-    Fn.WAVEFRONT_CHUNKS = int(__import__("os").environ.get("EDGEDICT_WAVEFRONT_CHUNKS", "4"))
+    Fn.WAVEFRONT_CHUNKS = int(__import__("os").environ.get("EDGEDICT_WAVEFRONT_CHUNKS", "6"))
     (y0, h0, c0, dx0, g0), (y1, h1, c1, dx1, g1) = res
     assert y0.shape == y1.shape
     assert rel_err(y1, y0) < 1e-5 and rel_err(h1, h0) < 1e-5 and rel_err(c1, c0) < 1e-5
