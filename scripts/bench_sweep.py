@@ -59,8 +59,44 @@ for T in (250, 500, 1000, 2000):
                  joint_gemm_tflops=round(2.0 * B * T * U1 * V * J / ms["gemm_bf16_nt"] / 1e9, 1),
                  joint_plus_loss_gbs=round((alg + 4 * N) / (loss_ms + ms["gemm_bf16_nt"]) / 1e6, 1),
                  loss_rel_err_vs_oracle=float("%.2e" % rel), finite=bool(torch.isfinite(costs).all()))
+        # ---- the path bench.py runs (bf16 mode): logits GEMM with the softmax statistics in its epilogue (bf16 logits),
+        # lattice, in-place bf16 gradient.  SURVEY 8(d): 4*s*N with the GEMM inside the region, s = 2.
+        del logits, grads, l4
+        torch.cuda.empty_cache()
+
+        def fused():
+            lg, ws = ops.joint_logits_lse(hid, w2, b2, lab, xl, yl, B, T, U1, 0)
+            costs = ops.rnnt_lattice(xl, yl, B, T, U1, ws)
+            ops.rnnt_loss_bwd_bf16(lg, lab, xl, yl, 0, ws, None, 1.0 / B)
+            return costs
+        for _ in range(2):
+            cf = fused()
+        torch.cuda.synchronize()
+        ops.PROF.reset(); ops.PROF.enabled = True
+        for _ in range(n):
+            cf = fused()
+        torch.cuda.synchronize()
+        pr = ops.PROF.summary(); ops.PROF.enabled = False
+        fm = {k: v["ms"] / n for k, v in pr.items()}
+        f_ms = fm["joint_logits_lse"] + fm["rnnt_loss_fwd"] + fm["rnnt_loss_bwd"]
+        # loss of the fused path against the C oracle on utterance 0 cropped to 24 x 12 cells (logits from the same
+        # bf16 operands, accumulated in fp64 on the host)
+        idx = (torch.arange(24, device="cuda")[:, None] * U1 + torch.arange(12, device="cuda")[None, :]).reshape(-1)
+        hs = hid[idx].contiguous()
+        one = lambda v: torch.tensor([v], dtype=torch.int32, device="cuda")
+        lgs, wss = ops.joint_logits_lse(hs, w2, b2, lab[:1, :11].contiguous(), one(24), one(11), 1, 24, 12, 0)
+        cs = ops.rnnt_lattice(one(24), one(11), 1, 24, 12, wss)
+        ref_logits = (hs.double().cpu() @ w2.double().cpu().t()).view(1, 24, 12, V).numpy()
+        co, _ = ol.logits(ref_logits, lab[:1, :11].cpu().numpy(), [24], [11], want_grads=False, dtype=np.float64)
+        r.update(fused_gemm_lse_ms=round(fm["joint_logits_lse"], 3), fused_lattice_ms=round(fm["rnnt_loss_fwd"], 3),
+                 fused_grad_ms=round(fm["rnnt_loss_bwd"], 3), fused_total_ms=round(f_ms, 3),
+                 fused_gbs=round(4 * 2 * N / f_ms / 1e6, 1), fused_frac_hbm=round(4 * 2 * N / f_ms / 1e6 / HBM, 3),
+                 fused_grad_gbs=round(2 * 2 * N / fm["rnnt_loss_bwd"] / 1e6, 1),
+                 fused_gemm_tflops=round(2.0 * N * J / fm["joint_logits_lse"] / 1e9, 1),
+                 fused_loss_rel_err_vs_oracle=float("%.2e" % (abs(float(cs[0]) - co[0]) / abs(co[0]))),
+                 fused_finite=bool(torch.isfinite(cf).all()))
         rows.append(r)
         print(json.dumps(r), flush=True)
-        del hid, logits, grads, l4
+        del hid
         torch.cuda.empty_cache()
 json.dump(dict(hbm_peak_gbs=HBM, rows=rows), open("gpurun_out/sweep.json", "w"), indent=1)
