@@ -253,6 +253,13 @@ def run_ours(args):
                         "training step; the tensor-pipe fraction is what the dependency chain leaves, the figure "
                         "to track is us_per_timestep" % cell_steps)
     roof["traffic"] = None
+    if top == "lstm_tc_bwd":
+        # one ncu capture of the BPTT kernel (profiles/r2/prof_r2_lstm_tc_bwd_noncluster.txt: 205.3 MB read + 46.6 MB
+        # written per 250-step launch, B = 32, H = 1024) scaled to this run's average launch length
+        per_step = (205.338368e6 + 46.582272e6) / 250.0
+        roof["traffic"] = round(per_step * roof["timesteps"] / max(1.0, kern[top]["calls_per_step"]))
+        roof["traffic_note"] = ("dram__bytes_read+write per launch from ncu (non-cluster variant, application replay), "
+                                "%.2f MB per timestep x the average launch length" % (per_step / 1e6))
     roof["peak_source"] = pk["src"] + (" (sustained)" if roof["bound"] == "tensor" else "")
     # the BASELINE.json side metric: joint+loss HBM fraction on the algorithmic bytes of SURVEY 8(d)
     n_logits = B * (T // 2) * (U + 1) * V
