@@ -40,6 +40,9 @@ template <int BN_, int EPW_ = 4, bool LOW_ = false> struct Cfg {
     static constexpr int STAGES = LOW_ ? 3 : (BN_ == 256 ? (EPW_ == 8 ? 3 : 4) : 5);
     static constexpr int B_BYTES = BN_ * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    // two accumulator buffers in TMEM (the epilogue of tile i overlaps the mainloop of tile i+1).  The co-resident
+    // configuration's 256 columns fit next to ONE lstm_c4 forward CTA (256 columns); lstm_c4 pads its shared-memory
+    // request so that a GEMM CTA is never placed next to two of them (a single-buffer variant measured 20 % slower).
     static constexpr int TMEM_COLS = 2 * BN_;
     static constexpr int EPI_BYTES = EPW_ * EPI_WARP_BYTES;
     static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + EPI_BYTES + 256;

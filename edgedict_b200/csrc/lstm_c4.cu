@@ -85,6 +85,29 @@ __device__ __forceinline__ void tmem_alloc32(uint32_t slot_saddr) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 32;" :: "r"(slot_saddr) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_alloc_n(uint32_t slot_saddr, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(slot_saddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_free_n(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(ncols) : "memory");
+}
+// 32 consecutive 32-bit columns of this thread's TMEM lane <- registers
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+        "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+        :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+           "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+           "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+           "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand read from TENSOR MEMORY (lane = row, two bf16 per 32-bit column along K)
+__device__ __forceinline__ void tc_mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+                 " tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n"
+                 :: "r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void tmem_free32(uint32_t taddr) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 32;" :: "r"(taddr) : "memory");
 }
@@ -111,22 +134,22 @@ __device__ __forceinline__ void cp_async16(uint32_t saddr, const void* gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(saddr), "l"(gmem) : "memory");
 }
 
-__device__ __forceinline__ uint4 ld_cg16(const void* p) {
-    uint4 v;
-    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
-    return v;
-}
-
+// TA: the W_hh slice lives in TENSOR MEMORY (A operand of tcgen05.mma from TMEM: 128 lanes x H/8 columns) instead of shared
+// memory: the MMAs stop re-reading 64 KB of shared memory per step (4 KB per MMA at 128 B/clk was what paced them, and two
+// co-resident CTAs shared that bandwidth) and the CTA's shared-memory footprint drops from 111 KB to 46 KB.
+// NACC: independent accumulators (k step j goes to accumulator j % NACC, summed by the epilogue): back-to-back tcgen05.mma
+// into ONE accumulator with N = 32 run at ~75 cycles each whatever the operand source -- a dependent chain, not a bandwidth limit.
+template <bool TA, int NACC>
 __global__ void __launch_bounds__(NGT, 2) lstm_c4_fwd_kernel(C4FwdP p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int H = p.H, B = p.B, T = p.T;
-    const int KS = H >> 2, NA = KS >> 6;                     // K slice per CTA, 64-wide swizzle atoms in it
+    const int KS = H >> 2, NA = TA ? 0 : (KS >> 6), NAT = KS >> 6;   // K slice per CTA, 64-wide swizzle atoms in it
     const int NC = H / UPC;
     const int CPR = KS >> 3;                                 // 16-byte chunks per row of the h slice (8 .. 32)
     const int NLD = CPR >> 2;                                // chunks per thread and step: 32 rows * CPR / 128
-    uint8_t* sA = smem;                                      // [NA][128 rows][128 B]   W_hh slice, resident
-    uint8_t* sB = sA + NA * 16384;                           // [NA][32 rows][128 B]    h_{t-1} slice of the step
+    uint8_t* sA = smem;                                      // [NA][128 rows][128 B]   W_hh slice, resident (not TA)
+    uint8_t* sB = sA + NA * 16384;                           // [NAT][32 rows][128 B]   h_{t-1} slice of the step
     float* stage = reinterpret_cast<float*>(sB + 16384);     // [4 dest][32 rows][32]   outgoing partial tiles (swz)
     float* recv = stage + 4 * 1024;                          // [3 src][32 rows][32]    incoming partial tiles (swz)
     uint64_t* bars = reinterpret_cast<uint64_t*>(recv + 3 * 1024);
@@ -137,8 +160,10 @@ __global__ void __launch_bounds__(NGT, 2) lstm_c4_fwd_kernel(C4FwdP p) {
     const int grp = (int)cluster_id_x();
     const int cta = grp * 4 + (int)rank;                     // owner of units [8 cta, 8 cta + 8)
     const unsigned ncta = gridDim.x;
+    const uint32_t acols = (KS / 2 <= 32) ? 32u : (KS / 2 <= 64) ? 64u : 128u;     // TMEM columns of the A slice (power of 2)
 
     // W_hh slice -> shared (row m = 32*dest_rank + 8*gate + unit; K-major, 128B swizzle)
+    if (!TA)
     for (int idx = tid; idx < 128 * CPR; idx += NGT) {
         const int m = idx / CPR, cc = idx - m * CPR;
         const int q = m >> 5, gate = (m >> 3) & 3, u = m & 7;
@@ -148,17 +173,40 @@ __global__ void __launch_bounds__(NGT, 2) lstm_c4_fwd_kernel(C4FwdP p) {
         *reinterpret_cast<uint4*>(sA + a * 16384 + m * 128 + ((c ^ (m & 7)) << 4)) = v;
     }
     if (tid == 0) {
-        mbar_init(accb, 1);
+        mbar_init(accb, NACC == 4 ? (uint32_t)NAT : 1u);     // one tcgen05.commit per issuing thread
         mbar_init(rbar, 1);                                  // one local arrive.expect_tx per step + 3 x 4 KB of copies
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) tmem_alloc32(smem_u32(tmem_slot));
+    if (warp == 0) {
+        if (TA) tmem_alloc_n(smem_u32(tmem_slot + 1), acols);
+        tmem_alloc_n(smem_u32(tmem_slot), 32u * NACC);
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
     fence_proxy_async();                                     // the A tile was written through the generic proxy
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     cluster_sync_all();                                      // peers' mbarriers exist before any copy completes on them
     const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_a = TA ? tmem_slot[1] : 0u;
+    if (TA) {
+        // row m = 32*warp + lane of the slice (gate = lane / 8, unit = lane % 8 of destination rank `warp`): its KS bf16 are
+        // KS/2 consecutive 32-bit TMEM columns of lane m (element k in the low half of column k/2 for even k)
+        const __nv_bfloat16* src = p.whh + ((size_t)(lane >> 3) * H + 32 * grp + 8 * warp + (lane & 7)) * H + (size_t)rank * KS;
+        for (int c0 = 0; c0 < KS / 2; c0 += 32) {
+            uint32_t r[32];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint4 v = *reinterpret_cast<const uint4*>(src + (size_t)(c0 + 4 * i) * 2);
+                r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
+            }
+            tc_st32(tmem_a + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+    }
 
     const int b = tid >> 2, up = tid & 3;
     const int j = cta * UPC + 2 * up;
@@ -222,14 +270,37 @@ __global__ void __launch_bounds__(NGT, 2) lstm_c4_fwd_kernel(C4FwdP p) {
             fence_proxy_async_smem();
         }
         __syncthreads();
-        if (tid == 0) {
+        if (NACC == 4) {
+            // One thread issues a tcgen05.mma every ~75 cycles whatever its size or operand source (measured: shared-memory
+            // or tensor-memory A, 1 / 2 / 4 accumulators all give 1230 cycles for 16 MMAs), so the K slice is issued by FOUR
+            // threads in parallel: lane 0 of warp a issues the four k steps of swizzle atom a into accumulator a and commits
+            // them itself (tcgen05.commit tracks the MMAs of the executing thread; the barrier counts NAT arrivals).
+            if (lane == 0 && warp < NAT) {
+                if (tid == 0) C4_STAMP(t, 1);
+                tc_fence_after();
+                const int a = warp;
+                const uint32_t d = tmem_base + (uint32_t)a * 32u;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (TA) tc_mma_bf16_ts(d, tmem_a + (uint32_t)(a * 4 + k) * 8u, make_desc(sb + a * 4096 + k * 32, 0, 1024), idesc, k ? 1u : 0u);
+                    else tc_mma_bf16(d, make_desc(sa + a * 16384 + k * 32, 0, 1024), make_desc(sb + a * 4096 + k * 32, 0, 1024), idesc,
+                                     k ? 1u : 0u);
+                }
+                tc_commit(accb);
+                if (tid == 0) { C4_STAMP(t, 2); mbar_expect_tx(rbar, 3 * 4096); }
+            }
+        } else if (tid == 0) {
             C4_STAMP(t, 1);
             tc_fence_after();
-            for (int a = 0; a < NA; ++a) {
+            for (int a = 0; a < NAT; ++a) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    tc_mma_bf16(tmem_base, make_desc(sa + a * 16384 + k * 32, 0, 1024),
-                                make_desc(sb + a * 4096 + k * 32, 0, 1024), idesc, (a | k) ? 1u : 0u);
+                for (int k = 0; k < 4; ++k) {
+                    const int j = a * 4 + k;
+                    const uint32_t d = tmem_base + (uint32_t)(j % NACC) * 32u, accum = j >= NACC ? 1u : 0u;
+                    if (TA) tc_mma_bf16_ts(d, tmem_a + (uint32_t)j * 8u, make_desc(sb + a * 4096 + k * 32, 0, 1024), idesc, accum);
+                    else tc_mma_bf16(d, make_desc(sa + a * 16384 + k * 32, 0, 1024),
+                                     make_desc(sb + a * 4096 + k * 32, 0, 1024), idesc, accum);
+                }
             }
             tc_commit(accb);
             C4_STAMP(t, 2);
@@ -243,6 +314,14 @@ __global__ void __launch_bounds__(NGT, 2) lstm_c4_fwd_kernel(C4FwdP p) {
         // the destination's mbarrier; per-thread st.shared::cluster pushes measured 2100 cycles against 1250)
         uint32_t r[32];
         tc_ld32(tmem_base + ((uint32_t)(warp * 32) << 16), r);
+#pragma unroll
+        for (int q = 1; q < NACC; ++q) {
+            if (NACC == 4 && q >= NAT) break;                // one accumulator per swizzle atom of the K slice
+            uint32_t r2[32];
+            tc_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)q * 32u, r2);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r2[i]));
+        }
         tc_fence_before();
 #pragma unroll
         for (int i = 0; i < 8; ++i)
@@ -317,7 +396,11 @@ __global__ void __launch_bounds__(NGT, 2) lstm_c4_fwd_kernel(C4FwdP p) {
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();                                      // no CTA exits while a peer may still address its smem
-    if (warp == 0) { tc_fence_after(); tmem_free32(tmem_base); }
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_free_n(tmem_base, 32u * NACC);
+        if (TA) tmem_free_n(tmem_a, acols);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -522,9 +605,26 @@ __global__ void __launch_bounds__(NTHR, CS == 8 ? 2 : 1) lstm_c4_bwd_kernel(cons
 // ---------------------------------------------------------------------------------------------------------
 inline bool c4_shape_ok(int B, int H) { return B >= 1 && H % 256 == 0 && H <= 1024; }
 
+inline int fwd_nacc() {             // independent accumulators of the forward MMAs: 1, 2 or 4 (EDGEDICT_C4_NACC)
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("EDGEDICT_C4_NACC"); v = e ? atoi(e) : 4; if (v != 1 && v != 2 && v != 4) v = 4; }
+    return v;
+}
+inline bool fwd_tmem_a() {          // W_hh slice in tensor memory (default) or in shared memory (EDGEDICT_C4_TMEMA=0)
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("EDGEDICT_C4_TMEMA"); v = (e && atoi(e) == 0) ? 0 : 1; }
+    return v == 1;
+}
 inline size_t fwd_smem(int H) {
-    const int NA = H / 256;
-    return 1024 + (size_t)NA * 16384 + 16384 + 7 * 4096 + 128;
+    const int NA = fwd_tmem_a() ? 0 : H / 256;
+    size_t b = 1024 + (size_t)NA * 16384 + 16384 + 7 * 4096 + 128;
+    // Tensor-memory budget: with the weights in TMEM a forward CTA holds up to 256 of the SM's 512 columns (128 A + 4 x 32
+    // accumulators).  Two of them fill the SM's tensor memory, and a co-resident GEMM CTA placed next to them would sit in
+    // tcgen05.alloc until a recurrence ends -- so the request is padded to 58 KB: two forward CTAs + the 115 KB
+    // co-resident GEMM configuration then exceed the SM's shared memory, and GEMM CTAs only land next to ONE forward CTA
+    // (256 + 128 columns).
+    if (fwd_tmem_a() && b < 58 * 1024) b = 58 * 1024;
+    return b;
 }
 template <int CS> size_t bwd_smem(int H) {
     const int NA = 4 * H / CS / 64;
@@ -591,10 +691,31 @@ int bwd_cs(int H) {
     return c;
 }
 
+// the forward kernel variant selected by the environment (TA x NACC)
+#define C4_FWD_DISPATCH(EXPR)                                                                        \
+    do {                                                                                             \
+        const int n_ = fwd_nacc();                                                                   \
+        if (fwd_tmem_a()) {                                                                          \
+            if (n_ == 1) { auto kern = lstm_c4_fwd_kernel<true, 1>; EXPR; }                          \
+            else if (n_ == 2) { auto kern = lstm_c4_fwd_kernel<true, 2>; EXPR; }                     \
+            else { auto kern = lstm_c4_fwd_kernel<true, 4>; EXPR; }                                  \
+        } else {                                                                                     \
+            if (n_ == 1) { auto kern = lstm_c4_fwd_kernel<false, 1>; EXPR; }                         \
+            else if (n_ == 2) { auto kern = lstm_c4_fwd_kernel<false, 2>; EXPR; }                    \
+            else { auto kern = lstm_c4_fwd_kernel<false, 4>; EXPR; }                                 \
+        }                                                                                            \
+    } while (0)
+
+int fwd_max_clusters(int H) {
+    int n = -1;
+    C4_FWD_DISPATCH(n = max_clusters_of(kern, H / 8, 4, fwd_smem(H), NGT));
+    return n;
+}
+
 bool fwd_ok(int H) {
     static int cache[5] = {-1, -1, -1, -1, -1};
     int& c = cache[H / 256];
-    if (c < 0) c = max_clusters_of(lstm_c4_fwd_kernel, H / 8, 4, fwd_smem(H), NGT) >= H / 32 ? 1 : 0;
+    if (c < 0) c = fwd_max_clusters(H) >= H / 32 ? 1 : 0;
     return c == 1;
 }
 
@@ -618,7 +739,7 @@ EB_API int eb_lstm_c4_set_trace(void* dev_buf, int steps) {
 // diagnostic: co-resident clusters of the kernels (which: 0 forward / clusters of 4, 4 or 8 backward with that cluster size)
 EB_API int eb_lstm_c4_max_clusters(int H, int which) {
     if (H % 256 || H > 1024 || H <= 0) return -1;
-    if (which == 0) return max_clusters_of(lstm_c4_fwd_kernel, H / 8, 4, fwd_smem(H), NGT);
+    if (which == 0) return fwd_max_clusters(H);
     if (which == 4) return max_clusters_of(lstm_c4_bwd_kernel<4>, H / 8, 4, bwd_smem<4>(H));
     if (which == 8) return max_clusters_of(lstm_c4_bwd_kernel<8>, H / 8, 8, bwd_smem<8>(H));
     return -1;
@@ -646,7 +767,11 @@ EB_API int eb_lstm_c4_fwd(const float* xg, const void* whh16, const float* h0, c
         return EB_ERR_INVALID;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const size_t smem = fwd_smem(H);
-    EB_CUDA(cudaFuncSetAttribute(lstm_c4_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        cudaError_t e_ = cudaSuccess;
+        C4_FWD_DISPATCH(e_ = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        EB_CUDA(e_);
+    }
     char* base = reinterpret_cast<char*>(scratch);
     const size_t tile_save = (size_t)T * (H / UPC) * NGT;
     for (int b0 = 0, tile = 0; b0 < B; b0 += NB, ++tile) {
@@ -668,7 +793,9 @@ EB_API int eb_lstm_c4_fwd(const float* xg, const void* whh16, const float* h0, c
         p.gates_std = gates_std ? gates_std + (size_t)b0 * T * 4 * H : nullptr;
         p.cseq_std = cseq_std ? cseq_std + (size_t)b0 * T * H : nullptr;
         EB_CUDA(cudaMemsetAsync(scratch, 0, C4_HDR, st));
-        if (!launch_clustered(lstm_c4_fwd_kernel, H / UPC, NGT, 4, smem, st, p)) return EB_ERR_CUDA;
+        bool ok = false;
+        C4_FWD_DISPATCH(ok = launch_clustered(kern, H / UPC, NGT, 4, smem, st, p));
+        if (!ok) return EB_ERR_CUDA;
     }
     return EB_OK;
 }
