@@ -252,8 +252,23 @@ __global__ void __launch_bounds__(NGT, 2) lstm_c4_fwd_kernel(C4FwdP p) {
         if (tid == 0) spin_wait_ge(wait_ctr, (unsigned)(t + 1) * nprod);   // (a back-off between polls changes nothing: measured)
         __syncthreads();
         if (tid == 0) C4_STAMP(t, 0);
-        // ---- A. pull this CTA's K slice of h_{t-1} (L2 -> registers -> swizzled shared tile)
-        {
+        // ---- A. pull this CTA's K slice of h_{t-1} (L2 -> swizzled shared tile)
+        if (NACC == 4) {
+            // warp a pulls swizzle atom a (32 rows x 64 k = 4 KB) and issues its MMAs as soon as ITS data is there: no
+            // block barrier between the pull and the MMAs
+            if (warp < NAT) {
+                const __nv_bfloat16* src = p.hx + (size_t)((t + 1) & 1) * xstride + (size_t)rank * KS + warp * 64;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int row = i * 4 + (lane >> 3), c = lane & 7;
+                    cp_async16(sb + (uint32_t)(warp * 4096 + row * 128 + ((c ^ (row & 7)) << 4)), src + (size_t)row * H + c * 8);
+                }
+                asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+                if (tid == 0) C4_STAMP(t, 9);
+                fence_proxy_async_smem();
+                __syncwarp();
+            }
+        } else {
             const __nv_bfloat16* src = p.hx + (size_t)((t + 1) & 1) * xstride + (size_t)rank * KS;
             // cp.async straight into the swizzled tile (register staging + st.shared measured 450 cycles slower)
 #pragma unroll
@@ -268,8 +283,8 @@ __global__ void __launch_bounds__(NGT, 2) lstm_c4_fwd_kernel(C4FwdP p) {
             asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
             if (tid == 0) C4_STAMP(t, 9);
             fence_proxy_async_smem();
+            __syncthreads();
         }
-        __syncthreads();
         if (NACC == 4) {
             // One thread issues a tcgen05.mma every ~75 cycles whatever its size or operand source (measured: shared-memory
             // or tensor-memory A, 1 / 2 / 4 accumulators all give 1230 cycles for 16 MMAs), so the K slice is issued by FOUR

@@ -440,6 +440,8 @@ __global__ void __launch_bounds__(NW * 32, 1) lstm_tc_bwd_kernel(BwdP p) {
         __syncthreads();
         TC_STAMP(T - 1 - t, 4);
         // ---- phase B: partial dh_rec[unit (JS), batch] over this CTA's K-slice of dG_t
+        // (staggering the warps' pulls by 64-192 cycles lets warp 0 start its HMMAs 900 cycles earlier but leaves the step unchanged:
+        //  the last warp's range arrives when it did before -- measured, removed)
         warp_pull(gs + ks0 * 16, KP, gcur + r0 + ks0 * 16, H4, myks * 2, NB);
         TC_STAMP(T - 1 - t, 5);
         float acc[MT][4][4];
