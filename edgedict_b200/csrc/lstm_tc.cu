@@ -301,13 +301,11 @@ long long* g_tc_trace = nullptr;
 int g_tc_trace_steps = 0;
 
 // REMAP selects the phase-A thread -> (unit, batch row) map:
-//   false (default, every measurement of round 1): unit = warp, row = lane.  A warp-wide load of a saved gate then
-//          touches 32 different 32-byte sectors (one per batch row) for 4 useful bytes each, and the 8 warps of the
-//          CTA re-touch the same sectors: ~1800 sector requests per CTA and step, as much L2 -> SM traffic as the
-//          exchange pull itself, issued right before it;
-//   true  (EDGEDICT_LSTM_BWD_REMAP=1; same arithmetic, NOT yet measured -- the round's GPU budget was spent when
-//          the access pattern was understood): unit = lane / 4, row = 4 * warp + lane % 4, the forward kernel's
-//          map: 8 consecutive units of a row = one sector, 4 sectors per load, ~220 requests per CTA and step.
+//   true  (default): unit = lane / 4, row = 4 * warp + lane % 4, the forward kernel's map: the 8 units of a row are one sector, a
+//          warp-wide load of a saved gate touches 4 sectors, and -- what counts on the critical path -- the exchange store of a warp
+//          is 4 rows x 64 contiguous bytes instead of 32 rows x 8 bytes: gate math + store 800 -> 350 cycles, the barrier behind it
+//          opens 800 cycles earlier (fewer write transactions to fence), 9807 -> 8544 cycles per step (profiles/r2);
+//   false (EDGEDICT_LSTM_BWD_REMAP=0, every measurement of round 1): unit = warp, row = lane: 32 sectors per load for 4 useful bytes each.
 template <int CS, bool CLUSTER, bool REMAP = false>
 __global__ void __launch_bounds__(NW * 32, 1) lstm_tc_bwd_kernel(BwdP p) {
     constexpr int MT = CS / 2;                               // m16 tiles: 8*CS units
@@ -550,7 +548,7 @@ size_t bwd_smem(int H) {
 
 inline bool bwd_remap() {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("EDGEDICT_LSTM_BWD_REMAP"); v = (e && atoi(e)) ? 1 : 0; }
+    if (v < 0) { const char* e = getenv("EDGEDICT_LSTM_BWD_REMAP"); v = (e && atoi(e) == 0) ? 0 : 1; }
     return v == 1;
 }
 
