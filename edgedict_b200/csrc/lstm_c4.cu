@@ -44,7 +44,8 @@ __device__ __forceinline__ void st_shared_f4(uint32_t saddr, uint32_t a, uint32_
 }
 constexpr int NGT = 128;          // gate threads (warps 0-3); warp 4 = barrier poller / TMA / MMA issuer
 constexpr int NTHR = 160;
-constexpr size_t C4_HDR = 1024;   // scratch: grid barrier counter
+constexpr size_t C4_HDR = 4096;   // scratch: grid barrier counters, one per K slice, 1 KB apart (different L2 slices)
+constexpr int CTR_STRIDE = 256;   // uints between two slice counters
 
 // debug stamps: slot s of step `step` <- clock64() (CTA 0 only; the pointer is null in production)
 __device__ __forceinline__ long long gtimer() {
@@ -226,8 +227,8 @@ __global__ void __launch_bounds__(NGT, 2) lstm_c4_fwd_kernel(C4FwdP p) {
     // [r*NC/4, (r+1)*NC/4): it waits for those arrivals alone (counter r, 128 bytes apart).  Every cluster consumes
     // all four slices, so no CTA can run a step ahead of any producer and the double-buffered exchange stays safe.
     const unsigned nprod = ncta >> 2;
-    unsigned* const my_ctr = p.bar + (cta / (int)nprod) * 32;
-    const unsigned* const wait_ctr = p.bar + rank * 32;
+    unsigned* const my_ctr = p.bar + (cta / (int)nprod) * CTR_STRIDE;
+    const unsigned* const wait_ctr = p.bar + rank * CTR_STRIDE;
     if (tid == 0) { __threadfence(); atomicAdd(my_ctr, 1u); }
     const float* xgp = p.xg + (size_t)b * T * 4 * H + j;
     float2 xr[4];
