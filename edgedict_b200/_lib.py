@@ -22,6 +22,7 @@ SIGNATURES = {
     "eb_gemm_f32": (I, [P, L, L, P, L, L, P, L, P, I, I, I, F, F, P]),
     "eb_gemm_bf16": (I, [P, I, P, I, P, I, P, I, L, I, L, P]),
     "eb_gemm_bf16_ex": (I, [P, I, P, I, P, I, P, I, L, I, L, I, P]),
+    "eb_gemm_pair_mode": (I, [I]),
     "eb_gemm_bf16_dtanh": (I, [P, I, P, I, P, P, L, I, L, P]),
     "eb_joint_dpre_reduce": (I, [P, P, P, I, I, I, I, P]),
     "eb_lstm_scratch_bytes": (Z, [I, I]),

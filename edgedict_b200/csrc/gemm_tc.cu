@@ -35,10 +35,13 @@ constexpr int EPI_WARP_BYTES = 32 * 36 * 4;
 // LOW_ = "co-resident" configuration: 3 stages of the narrow tile (115 KB of shared memory), so that a GEMM CTA
 // fits on an SM next to one CTA of a persistent recurrent kernel (lstm_tc.cu) -- used by the layer-wavefront
 // schedule of the encoder stack, where the input GEMM of one layer runs under the recurrence of another.
-template <int BN_, int EPW_ = 4, bool LOW_ = false> struct Cfg {
+// PAIR_ = cta_group::2: two CTAs of a cluster (one TPC) work on one 256 x 256 tile -- each owns 128 rows of it and
+// stages its own A rows plus HALF of the B tile (the tensor cores of both SMs read both halves), so a 128 x 256 x 64
+// block costs each SM 32 KB of L2 -> SM traffic instead of 48 KB; the pair's leader issues every MMA.
+template <int BN_, int EPW_ = 4, bool LOW_ = false, bool PAIR_ = false> struct Cfg {
     static constexpr int NTHREADS = 64 + 32 * EPW_;
-    static constexpr int STAGES = LOW_ ? 3 : (BN_ == 256 ? (EPW_ == 8 ? 3 : 4) : 5);
-    static constexpr int B_BYTES = BN_ * BK * 2;
+    static constexpr int STAGES = PAIR_ ? (EPW_ == 8 ? 5 : 6) : LOW_ ? 3 : (BN_ == 256 ? (EPW_ == 8 ? 3 : 4) : 5);
+    static constexpr int B_BYTES = (PAIR_ ? BN_ / 2 : BN_) * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     // two accumulator buffers in TMEM (the epilogue of tile i overlaps the mainloop of tile i+1).  The co-resident
     // configuration's 256 columns fit next to ONE lstm_c4 forward CTA (256 columns); lstm_c4 pads its shared-memory
@@ -58,15 +61,16 @@ template <int BN_, int EPW_ = 4, bool LOW_ = false> struct Cfg {
 //   else the plain round-robin over output tiles.
 struct Sched {
     long num_m; int num_n; int ksplit; long out_tiles; bool n_inner;
+    unsigned wid, nw;                                        // this worker (CTA, or CTA pair) and the number of workers
     __device__ __forceinline__ long count() const { return out_tiles * ksplit; }
     __device__ __forceinline__ bool get(long j, long& m_blk, int& n_blk, int& ks) const {
         if (n_inner) {
-            const long grp = (long)blockIdx.x + (j / num_n) * gridDim.x;
+            const long grp = (long)wid + (j / num_n) * nw;
             if (grp >= num_m) return false;
             m_blk = grp; n_blk = (int)(j % num_n); ks = 0;
             return true;
         }
-        const long wi = (long)blockIdx.x + j * gridDim.x;
+        const long wi = (long)wid + j * nw;
         if (wi >= out_tiles * ksplit) return false;
         const long tile = wi % out_tiles;
         ks = (int)(wi / out_tiles);
@@ -91,12 +95,13 @@ struct LseArgs {
 // A_MN / B_MN: operand stored with its M (resp. N) index contiguous ("MN-major"), else K contiguous.
 //   K-major tile in smem : [128 rows][64 k] bf16, 128 B per row, 128B swizzle; SBO = 1024 (8 rows)
 //   MN-major tile in smem: 2 x [64 k][64 mn] bf16, 128 B per k-row; SBO = 1024 (8 k-rows), LBO = 8192
-template <bool A_MN, bool B_MN, int BN_, bool LSE = false, int EPW_ = 4, bool LOW_ = false>
+template <bool A_MN, bool B_MN, int BN_, bool LSE = false, int EPW_ = 4, bool LOW_ = false, bool PAIR_ = false>
 __global__ void __launch_bounds__(64 + 32 * EPW_, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                void* __restrict__ Cout, int c_bf16, const float* __restrict__ bias, int accumulate,
                long M, int N, long K, int ksplit, LseArgs lse = LseArgs()) {
-    using C_ = Cfg<BN_, EPW_, LOW_>;
+    using C_ = Cfg<BN_, EPW_, LOW_, PAIR_>;
+    static_assert(!PAIR_ || BN_ == 256, "the pair tile is 256 x 256");
     constexpr int BN = BN_, STAGES = C_::STAGES, STAGE_BYTES = C_::STAGE_BYTES;
     constexpr int TMEM_COLS = C_::TMEM_COLS, EPI_BYTES = C_::EPI_BYTES;
     extern __shared__ uint8_t smem_raw[];
@@ -110,28 +115,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long num_m = (M + BM - 1) / BM;
+    constexpr int TM = PAIR_ ? 2 * BM : BM;                  // rows of one work item (a pair's tile is 256 rows)
+    const uint32_t rank = PAIR_ ? cluster_ctarank() : 0u;    // 0 = the pair's leader (MMA issuer)
+    const long num_m = (M + TM - 1) / TM;
     const int num_n = (N + BN - 1) / BN;
     Sched sch;
     sch.num_m = num_m; sch.num_n = num_n; sch.ksplit = ksplit; sch.out_tiles = num_m * num_n;
-    sch.n_inner = LSE || ((ksplit == 1) && (num_m >= 2L * gridDim.x));   // LSE needs a row block's tiles back to back
+    sch.wid = PAIR_ ? blockIdx.x >> 1 : blockIdx.x; sch.nw = PAIR_ ? gridDim.x >> 1 : gridDim.x;
+    sch.n_inner = LSE || ((ksplit == 1) && (num_m >= 2L * sch.nw));   // LSE needs a row block's tiles back to back
     const int nkb_total = (int)((K + BK - 1) / BK);
     const int kb_per = (nkb_total + ksplit - 1) / ksplit;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, EPW_); }
+        // pair: the leader's tmem_empty collects the epilogue warps of both CTAs; full[] is used in the leader only
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, PAIR_ ? 2 * EPW_ : EPW_); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tma_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tma_b) : "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                     :: "r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (PAIR_) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                         :: "r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                         :: "r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR_) cluster_sync_all();                           // the peer's mbarriers exist before anything arrives on them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -141,38 +157,62 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             long mb; int nb, ksx;
             for (long jj = 0; sch.get(jj, mb, nb, ksx); ++jj) {
                 const int kb0 = ksx * kb_per, kb1 = min(nkb_total, kb0 + kb_per);
-                const int m0 = (int)mb * BM, n0 = nb * BN;
+                const int m0 = ((int)mb * (TM / BM) + (int)rank) * BM, n0 = nb * BN;
+                // a wide tile hanging over the last columns (N % 256 == 128) runs its MMAs 128 wide: MN-major B then
+                // needs half the boxes (K-major boxes are fixed by the tensor map; the unused rows arrive as zeros)
+                const int ninst = min(BN, ((N - n0 + 127) >> 7) << 7);
+                const int nbox = (PAIR_ ? ninst / 2 : ninst) / 64;
+                const uint32_t tx = A_BYTES + (B_MN ? (uint32_t)nbox * 8192u : (uint32_t)C_::B_BYTES);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(empty0 + 8 * stage, phase ^ 1);
-                    const uint32_t fb = full0 + 8 * stage;
-                    mbar_expect_tx(fb, STAGE_BYTES);
                     const uint32_t sa = smem_u32(tiles + stage * STAGE_BYTES), sb = sa + A_BYTES;
+                    if (PAIR_) {
+                        // both CTAs' bytes complete on the LEADER's full barrier (its producer expects 2 stages' worth)
+                        const uint32_t fbl = map_to_rank(full0 + 8 * stage, 0);
+                        if (rank == 0) mbar_expect_tx(full0 + 8 * stage, 2 * tx);
+                        const int nh = n0 + (int)rank * (ninst / 2);    // this CTA's half of the B tile
+                        if (!A_MN) tma_load_2d_pair(sa, &tma_a, kb * BK, m0, fbl);
+                        else { tma_load_2d_pair(sa, &tma_a, m0, kb * BK, fbl); tma_load_2d_pair(sa + 8192, &tma_a, m0 + 64, kb * BK, fbl); }
+                        if (!B_MN) tma_load_2d_pair(sb, &tma_b, kb * BK, nh, fbl);
+                        else {
+#pragma unroll
+                            for (int bx = 0; bx < BN / 128; ++bx)
+                                if (bx < nbox) tma_load_2d_pair(sb + bx * 8192, &tma_b, nh + bx * 64, kb * BK, fbl);
+                        }
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
+                    const uint32_t fb = full0 + 8 * stage;
+                    mbar_expect_tx(fb, tx);
                     if (!A_MN) tma_load_2d(sa, &tma_a, kb * BK, m0, fb);
                     else { tma_load_2d(sa, &tma_a, m0, kb * BK, fb); tma_load_2d(sa + 8192, &tma_a, m0 + 64, kb * BK, fb); }
                     if (!B_MN) tma_load_2d(sb, &tma_b, kb * BK, n0, fb);
                     else {
 #pragma unroll
-                        for (int bx = 0; bx < BN / 64; ++bx) tma_load_2d(sb + bx * 8192, &tma_b, n0 + bx * 64, kb * BK, fb);
+                        for (int bx = 0; bx < BN / 64; ++bx)
+                            if (bx < nbox) tma_load_2d(sb + bx * 8192, &tma_b, n0 + bx * 64, kb * BK, fb);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (lane == 0 && rank == 0) {
             // instruction descriptor: D=f32 (1<<4), A=B=bf16 (1<<7, 1<<10), majors @15/@16, N>>3 @17, M>>4 @24
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) |
-                                   ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) |
-                                   ((uint32_t)(BM >> 4) << 24);
+            const uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) |
+                                    ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(TM >> 4) << 24);
             int stage = 0; uint32_t phase = 0;
             long it = 0;
             long mb; int nb, ksx;
             for (long jj = 0; sch.get(jj, mb, nb, ksx); ++jj, ++it) {
                 const int kb0 = ksx * kb_per, kb1 = min(nkb_total, kb0 + kb_per);
                 const uint32_t acc = (uint32_t)(it & 1), acc_phase = (uint32_t)((it >> 1) & 1);
-                mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
+                if (PAIR_) mbar_wait_cluster(tempty0 + 8 * acc, acc_phase ^ 1);     // arrivals come from both CTAs
+                else mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
+                const int ninst = min(BN, ((N - nb * BN + 127) >> 7) << 7);       // see the producer
+                const uint32_t idesc = idesc0 | ((uint32_t)(ninst >> 3) << 17);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(full0 + 8 * stage, phase);
                     tc_fence_after();
@@ -181,12 +221,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         const uint64_t ad = A_MN ? make_desc(sa + k * 2048, 8192, 1024) : make_desc(sa + k * 32, 0, 1024);
                         const uint64_t bd = B_MN ? make_desc(sb + k * 2048, 8192, 1024) : make_desc(sb + k * 32, 0, 1024);
-                        tc_mma_bf16(d_tmem, ad, bd, idesc, ((kb - kb0) | k) ? 1u : 0u);
+                        if (PAIR_) tc_mma_bf16_pair(d_tmem, ad, bd, idesc, ((kb - kb0) | k) ? 1u : 0u);
+                        else tc_mma_bf16(d_tmem, ad, bd, idesc, ((kb - kb0) | k) ? 1u : 0u);
                     }
-                    tc_commit(empty0 + 8 * stage);          // frees the smem stage when the MMAs retire
+                    // frees the smem stage (pair: in both CTAs) when the MMAs retire
+                    if (PAIR_) tc_commit_pair(empty0 + 8 * stage); else tc_commit(empty0 + 8 * stage);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                tc_commit(tfull0 + 8 * acc);                // accumulator complete -> epilogue
+                // accumulator complete -> epilogue (pair: of both CTAs)
+                if (PAIR_) tc_commit_pair(tfull0 + 8 * acc); else tc_commit(tfull0 + 8 * acc);
             }
         }
     } else {
@@ -207,7 +250,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         for (long jj = 0; sch.get(jj, mb, nb, ks); ++jj, ++it) {
             const bool empty_split = ks * kb_per >= nkb_total;      // (only when K is tiny) nothing accumulated
             const uint32_t acc = (uint32_t)(it & 1), acc_phase = (uint32_t)((it >> 1) & 1);
-            const long m0 = mb * BM;
+            const long m0 = (mb * (TM / BM) + rank) * BM;
             const int n0 = nb * BN;
             const bool full_m = vec_ok && (m0 + BM <= M);
             if (LSE && nb == 0) {                                 // new row block: reset, decode (b,t,u) of my row
@@ -222,16 +265,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     if (cell_ok && u < Un - 1) lab = lse.labels[b * (lse.maxU - 1) + u];
                 }
             }
+            // 32-column chunks of this warp: c_begin, c_begin + CSTEP, ... < c_end.  A wide tile may hang over the last
+            // columns (N % 256 == 128): chunks past N are skipped, chunks inside keep the vector path.
+            constexpr int CSTEP = EPW_ == 8 ? 2 : 1;
+            const int c_begin = EPW_ == 8 ? chalf : 0;
+            const int c_end = LSE ? BN / 32 : min(BN / 32, (N - n0 + 31) >> 5);
+            const uint32_t t_tile = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+            // the latencies of one chunk -- TMEM load, bias (LSE) / tanh' operand (aux) fetch -- are taken off the warp's
+            // critical path by fetching for the NEXT chunk while the current one is processed (two warps per scheduler
+            // cannot hide them: 24 % / 31 % of the epilogue's stall samples before this)
+            const bool aux_fast = !LSE && c_bf16 && lse.aux && full_m && ksplit == 1 && !accumulate;
+            auto aux_fetch = [&](const int c, uint2 (&hq)[8]) {
+                if (!(aux_fast && n0 + c * 32 + 32 <= N)) return;
+                const __nv_bfloat16* ap = lse.aux + (m0 + q * 32 + rsub) * N + (n0 + c * 32 + c4 * 4);
+#pragma unroll
+                for (int rr = 0; rr < 8; ++rr) hq[rr] = __ldg(reinterpret_cast<const uint2*>(ap + (long)(rr * 4) * N));
+            };
+            const bool bias_fast = LSE && bias && bias_vec;
+            float bq[32];                                        // LSE: bias of the chunk about to be processed
+            auto bias_fetch = [&](const int c) {
+                if (!(bias_fast && n0 + c * 32 + 32 <= N)) return;
+#pragma unroll
+                for (int i4 = 0; i4 < 8; ++i4) {
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n0 + c * 32 + i4 * 4));
+                    bq[i4 * 4] = b4.x; bq[i4 * 4 + 1] = b4.y; bq[i4 * 4 + 2] = b4.z; bq[i4 * 4 + 3] = b4.w;
+                }
+            };
+            uint2 ha[8], hb[8];
+            if (c_begin < c_end) { aux_fetch(c_begin, ha); if (LSE) bias_fetch(c_begin); }
             mbar_wait(tfull0 + 8 * acc, acc_phase);
             tc_fence_after();
-#pragma unroll 1
-            for (int c = (EPW_ == 8 ? chalf : 0); c < BN / 32; c += (EPW_ == 8 ? 2 : 1)) {
-                // a wide tile may hang over the last columns (N % 256 == 128): chunks past N are skipped, chunks
-                // inside keep the vector path
-                if (!LSE && n0 + c * 32 >= N) break;
+            auto process = [&](const int c, uint32_t (&r)[32], uint2 (&hq)[8], uint2 (&hq_next)[8]) {
                 const bool full = full_m && (n0 + c * 32 + 32 <= N);
-                uint32_t r[32];
-                tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c * 32, r);
+                if (c + CSTEP < c_end) aux_fetch(c + CSTEP, hq_next);
                 if (empty_split) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) r[i] = 0u;
@@ -240,7 +306,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     const int col0 = n0 + c * 32;
                     constexpr float LOG2E = 1.4426950408889634f;
                     float cm = -INFINITY;
-                    if (col0 + 32 <= N && bias_vec) {             // whole chunk inside the vocabulary: no per-element guards
+                    if (col0 + 32 <= N && bias_fast) {            // bias prefetched while the previous chunk was processed
+#pragma unroll
+                        for (int i4 = 0; i4 < 8; ++i4) {
+                            const float v0 = __uint_as_float(r[i4 * 4]) + bq[i4 * 4], v1 = __uint_as_float(r[i4 * 4 + 1]) + bq[i4 * 4 + 1];
+                            const float v2 = __uint_as_float(r[i4 * 4 + 2]) + bq[i4 * 4 + 2], v3 = __uint_as_float(r[i4 * 4 + 3]) + bq[i4 * 4 + 3];
+                            r[i4 * 4] = __float_as_uint(v0); r[i4 * 4 + 1] = __float_as_uint(v1);
+                            r[i4 * 4 + 2] = __float_as_uint(v2); r[i4 * 4 + 3] = __float_as_uint(v3);
+                            cm = fmaxf(fmaxf(cm, fmaxf(v0, v1)), fmaxf(v2, v3));
+                        }
+                        if (c + CSTEP < c_end) bias_fetch(c + CSTEP);
+                    } else if (col0 + 32 <= N && bias_vec) {      // whole chunk inside the vocabulary: no per-element guards
 #pragma unroll
                         for (int i4 = 0; i4 < 8; ++i4) {
                             const float4 b4 = bias ? __ldg(reinterpret_cast<const float4*>(bias + col0 + i4 * 4))
@@ -302,11 +378,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                                  : "=f"(vv[rr].x), "=f"(vv[rr].y), "=f"(vv[rr].z), "=f"(vv[rr].w)
                                  : "r"(sbuf + (uint32_t)((rr * 4 + rsub) * 36 + c4 * 4) * 4));
                 if (full && ksplit == 1 && !accumulate) {         // the common case, free of per-store mode tests
-                    if (c_bf16 && !LSE && lse.aux) {
-                        uint2 hq[8];
-#pragma unroll
-                        for (int rr = 0; rr < 8; ++rr)
-                            hq[rr] = __ldg(reinterpret_cast<const uint2*>(lse.aux + (row0 + rr * 4) * N + col));
+                    if (c_bf16 && !LSE && lse.aux) {              // (== aux_fast here: hq was fetched one chunk ahead)
 #pragma unroll
                         for (int rr = 0; rr < 8; ++rr) {
                             const float4 v = vv[rr];
@@ -396,6 +468,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     }
                 }
                 __syncwarp();
+            };
+            uint32_t ra[32], rb[32];
+            if (c_begin < c_end) tc_ld32_issue(t_tile + c_begin * 32, ra);
+#pragma unroll 1
+            for (int c = c_begin; c < c_end; c += 2 * CSTEP) {
+                tc_ld_wait(ra);
+                const bool more = c + CSTEP < c_end;
+                if (more) tc_ld32_issue(t_tile + (c + CSTEP) * 32, rb);
+                process(c, ra, ha, hb);
+                if (more) {
+                    tc_ld_wait(rb);
+                    if (c + 2 * CSTEP < c_end) tc_ld32_issue(t_tile + (c + 2 * CSTEP) * 32, ra);
+                    process(c + CSTEP, rb, hb, ha);
+                }
             }
             if (LSE && nb == num_n - 1) {                         // whole vocabulary seen: publish the row statistics
                 if (EPW_ == 8) {
@@ -425,14 +511,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 }
             }
             tc_fence_before();
-            if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+            if (lane == 0) {
+                if (PAIR_) mbar_arrive_remote(map_to_rank(tempty0 + 8 * acc, 0));
+                else mbar_arrive(tempty0 + 8 * acc);
+            }
         }
     }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR_) cluster_sync_all();                           // neither CTA's shared / tensor memory goes away under the other
+    else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        if (PAIR_) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
 
@@ -510,6 +601,43 @@ int launch_low(const CUtensorMap& ta, const CUtensorMap& tb, void* C, int c_bf16
     return EB_OK;
 }
 
+// cta_group::2 configuration (see Cfg): clusters of two CTAs, one 256 x 256 tile per pair, 8 epilogue warps per CTA.
+// mode: EDGEDICT_GEMM_PAIR / eb_gemm_pair_mode -- -1 auto (bf16-output GEMMs with many row blocks), 0 never, 1 whenever legal
+int g_pair_mode = -2;
+int pair_mode() {
+    if (g_pair_mode == -2) { const char* e = getenv("EDGEDICT_GEMM_PAIR"); g_pair_mode = e ? atoi(e) : -1; }
+    return g_pair_mode;
+}
+
+template <bool B_MN, bool LSE>
+int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, void* C, int c_bf16, const float* bias, int accumulate,
+                long M, int N, long K, const LseArgs& ea, cudaStream_t st) {
+    using C_ = Cfg<256, 8, false, true>;
+    auto kern = gemm_tc_kernel<false, B_MN, 256, LSE, 8, false, true>;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(C_::NTHREADS); cfg.dynamicSmemBytes = C_::SMEM_BYTES; cfg.stream = st;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    static int max_pairs = 0;
+    if (!max_pairs) {
+        EB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM_BYTES));
+        cfg.gridDim = dim3(2 * (eb_num_sms() / 2));
+        int n = 0;
+        EB_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+        if (n <= 0) return EB_ERR_CUDA;
+        max_pairs = n < eb_num_sms() / 2 ? n : eb_num_sms() / 2;
+    }
+    const long work = ((M + 255) / 256) * (LSE ? 1 : (N + 255) / 256);
+    const int pairs = (int)(work < max_pairs ? work : max_pairs);
+    cfg.gridDim = dim3(2 * pairs);
+    int c16 = c_bf16, acc = accumulate, ks1 = 1;
+    EB_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, C, c16, bias, acc, M, N, K, ks1, ea));
+    EB_CHECK_LAUNCH();
+    return EB_OK;
+}
+
 template <int BN_>
 int launch_lse(const CUtensorMap& ta, const CUtensorMap& tb, void* C, const float* bias, long M, int N, long K,
                const LseArgs& lse, cudaStream_t st) {
@@ -545,8 +673,13 @@ EB_API int eb_joint_logits_lse(const void* hidden16, const void* w2_16, const fl
         return EB_ERR_INVALID;
     const long M = (long)B * maxT * maxU;
     const bool wide = (V % 256 == 0);
+    // cta_group::2 tiles only on request: measured at E6D2 (profiles/r2/prof_r2_gemm_pair.txt) they cut the L2 -> SM
+    // operand traffic by a third (15.9 -> 10.6 GB per launch) but not the time (1.35 vs 1.37-1.43 ms): with the epilogue
+    // switched off the mainloop alone runs at ~1400 TFLOP/s either way, the softmax epilogue's cost is added on top
+    const bool pair = wide && pair_mode() == 1;
     CUtensorMap ta, tb;
-    if (!make_map(&ta, hidden16, (uint64_t)J, (uint64_t)M, 128) || !make_map(&tb, w2_16, (uint64_t)J, (uint64_t)V, wide ? 256 : 128)) {
+    if (!make_map(&ta, hidden16, (uint64_t)J, (uint64_t)M, 128) ||
+        !make_map(&tb, w2_16, (uint64_t)J, (uint64_t)V, (wide && !pair) ? 256 : 128)) {
         fprintf(stderr, "[edgedict_b200] cuTensorMapEncodeTiled failed\n");
         return EB_ERR_CUDA;
     }
@@ -554,7 +687,14 @@ EB_API int eb_joint_logits_lse(const void* hidden16, const void* w2_16, const fl
     lse.labels = labels; lse.xlen = xlen; lse.ylen = ylen; lse.denom = denom; lse.lpb = lpb; lse.lpl = lpl;
     lse.maxT = maxT; lse.maxU = maxU; lse.blank = blank;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (pair) return launch_pair<false, true>(ta, tb, logits16, 1, b2, 0, M, V, J, lse, st);
     return wide ? launch_lse<256>(ta, tb, logits16, b2, M, V, J, lse, st) : launch_lse<128>(ta, tb, logits16, b2, M, V, J, lse, st);
+}
+
+EB_API int eb_gemm_pair_mode(int mode) {
+    const int prev = pair_mode();
+    g_pair_mode = mode < 0 ? -1 : (mode ? 1 : 0);
+    return prev;
 }
 
 EB_API int eb_gemm_bf16(const void* A, int a_mn_major, const void* B, int b_mn_major, void* C, int c_bf16,
@@ -603,16 +743,28 @@ static int gemm_dispatch(const void* A, int a_mn_major, const void* B, int b_mn_
     if (force_bn == 128) wide = false;
     if (force_bn == 256 && N % 128 == 0) wide = true;
     if (low) wide = false;
+    if (pair_mode() == 1 && c_bf16 && !a_mn_major && !low && N % 128 == 0 && N >= 256) wide = true;   // (tests) any legal shape
+    // cta_group::2 pairs: bf16 outputs (no split-K), A K-major, wide tiles.  Automatic for the MN-major-B product with
+    // enough 256-row blocks for every pair -- the joint's d-hidden GEMM, 1.53 -> 1.38 ms at E6D2 -- and on request
+    // (mode 1) for any legal shape; the K-major-B products measured no faster (see eb_joint_logits_lse).
+    const bool pair = wide && c_bf16 && !a_mn_major &&
+                      (pair_mode() == 1 || (pair_mode() < 0 && b_mn_major && (M + 255) / 256 >= 2L * (eb_num_sms() / 2)));
     CUtensorMap ta, tb;
     bool ok = a_mn_major ? make_map(&ta, A, (uint64_t)M, (uint64_t)K, 64) : make_map(&ta, A, (uint64_t)K, (uint64_t)M, 128);
     ok = ok && (b_mn_major ? make_map(&tb, B, (uint64_t)N, (uint64_t)K, 64)
-                           : make_map(&tb, B, (uint64_t)K, (uint64_t)N, wide ? 256 : 128));
+                           : make_map(&tb, B, (uint64_t)K, (uint64_t)N, (wide && !pair) ? 256 : 128));
     if (!ok) {
         fprintf(stderr, "[edgedict_b200] cuTensorMapEncodeTiled failed\n");
         return EB_ERR_CUDA;
     }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (low) return launch_low(ta, tb, C, c_bf16, bias, accumulate, M, N, K, st);
+    if (pair) {
+        LseArgs ea = LseArgs();
+        ea.aux = reinterpret_cast<const __nv_bfloat16*>(aux);
+        return b_mn_major ? launch_pair<true, false>(ta, tb, C, c_bf16, bias, accumulate, M, N, K, ea, st)
+                          : launch_pair<false, false>(ta, tb, C, c_bf16, bias, accumulate, M, N, K, ea, st);
+    }
 #define EB_GO(AM, BMN)                                                                              \
     return wide ? launch<AM, BMN, 256>(ta, tb, C, c_bf16, bias, accumulate, M, N, K, st, aux)      \
                 : launch<AM, BMN, 128>(ta, tb, C, c_bf16, bias, accumulate, M, N, K, st, aux)

@@ -124,6 +124,12 @@ def gemm_f32(A, sam, sak, B, sbk, sbn, M, N, K, bias=None, out=None, beta=0.0, a
 GEMM_CORESIDENT = 1      # include/edgedict_b200.h EB_GEMM_CORESIDENT
 
 
+def gemm_pair_mode(mode):
+    """-1 automatic / 0 never / 1 whenever legal: cta_group::2 tiles in the bf16-output GEMMs (eb_gemm_pair_mode);
+    returns the previous mode."""
+    return int(lib().eb_gemm_pair_mode(int(mode)))
+
+
 def gemm_bf16(A, a_mn, B, b_mn, M, N, K, bias=None, out=None, out_bf16=False, accumulate=False, tag=None, flags=0):
     if out is None:
         out = torch.empty(M, N, dtype=bf16 if out_bf16 else f32, device=A.device)

@@ -91,6 +91,55 @@ def test_gemm_bf16_wide_tiles_overhanging_the_last_columns():
     assert rel_err(y3.float().cpu(), ((dy.float() @ w_nn.float()) * (1 - hid.float() ** 2)).cpu()) < 1e-2
 
 
+def test_gemm_bf16_cta_pair_tiles_match_one_cta_tiles():
+    """cta_group::2 tiles (two CTAs of a cluster on one 256 x 256 tile, each staging half of B; eb_gemm_pair_mode) give
+    the bits of the one-CTA tiles -- same MMA order per output element -- for the three bf16-output products of the
+    joint: plain nt + bias (and accumulate), d-hidden with tanh' (B MN-major), logits + softmax statistics; odd row-block
+    counts (the peer CTA of the last pair has no rows), N = 256 k + 128 (128-wide MMAs on the last column tile)."""
+    from edgedict_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(11)
+    rn = lambda *s: torch.randn(*s, device="cuda", generator=g)
+
+    def both(fn):
+        prev = ops.gemm_pair_mode(0)
+        try:
+            one = fn()
+            ops.gemm_pair_mode(1)
+            two = fn()
+        finally:
+            ops.gemm_pair_mode(prev)
+        return one, two
+
+    for (M, N, K) in [(256 * 5, 512, 320), (128 * 7 + 40, 640, 192), (128 * 301, 1024, 640)]:
+        A, W, bias = (rn(M, K) * 0.5).bfloat16(), (rn(N, K) * 0.1).bfloat16(), rn(N)
+        one, two = both(lambda: ops.gemm_bf16(A, 0, W, 0, M, N, K, bias=bias, out_bf16=True))
+        assert torch.equal(one, two)
+        assert rel_err(two.float().cpu(), (A.float() @ W.float().t() + bias).cpu()) < 1e-2
+        base = rn(M, N).bfloat16()
+        one, two = both(lambda: ops.gemm_bf16(A, 0, W, 0, M, N, K, out=base.clone(), accumulate=True))
+        assert torch.equal(one, two)
+        Wn, hid = (rn(K, N) * 0.1).bfloat16(), torch.tanh(rn(M, N)).bfloat16()
+        one, two = both(lambda: ops.gemm_bf16_dtanh(A, Wn, True, hid, M, N, K))
+        assert torch.equal(one, two)
+        assert rel_err(two.float().cpu(), ((A.float() @ Wn.float()) * (1 - hid.float() ** 2)).cpu()) < 1e-2
+    for (B, T, U, V, J) in [(3, 37, 9, 512, 128), (2, 150, 33, 1024, 640)]:
+        hid, w2, b2 = torch.tanh(rn(B, T, U, J)).bfloat16(), (rn(V, J) * 0.2).bfloat16(), rn(V)
+        labels = torch.randint(1, V, (B, U - 1), dtype=torch.int32, device="cuda", generator=g)
+        xlen = torch.randint(T // 2, T + 1, (B,), dtype=torch.int32, device="cuda", generator=g)
+        ylen = torch.randint(1, U, (B,), dtype=torch.int32, device="cuda", generator=g)
+        xlen[0], ylen[0] = T, U - 1
+        (l0, w0), (l1, w1) = both(lambda: ops.joint_logits_lse(hid, w2, b2, labels, xlen, ylen, B, T, U, 0))
+        assert torch.equal(l0, l1)
+        n = B * T * U
+        ok = ((torch.arange(T, device="cuda")[None, :, None] < xlen[:, None, None]) &
+              (torch.arange(U, device="cuda")[None, None, :] <= ylen[:, None, None])).reshape(-1)
+        s0 = w0.view(torch.float32)[:3 * n].view(3, n)[:, ok]
+        s1 = w1.view(torch.float32)[:3 * n].view(3, n)[:, ok]
+        assert torch.equal(s0, s1)
+        den = -torch.logsumexp(hid.float().view(n, J) @ w2.float().t() + b2, dim=1)
+        assert float((s1[0] - den[ok]).abs().max()) < 2e-3
+
+
 @pytest.mark.parametrize("rows,H,res", [(7, 12, False), (33, 240, False), (64, 320, True), (19, 1024, True), (5, 1500, True),
                                         (300, 256, False), (2000, 512, True), (4100, 1024, False), (3, 128, True)])
 def test_layernorm_fwd_bwd(rows, H, res):
