@@ -265,39 +265,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     if (cell_ok && u < Un - 1) lab = lse.labels[b * (lse.maxU - 1) + u];
                 }
             }
-            // 32-column chunks of this warp: c_begin, c_begin + CSTEP, ... < c_end.  A wide tile may hang over the last
-            // columns (N % 256 == 128): chunks past N are skipped, chunks inside keep the vector path.
-            constexpr int CSTEP = EPW_ == 8 ? 2 : 1;
-            const int c_begin = EPW_ == 8 ? chalf : 0;
-            const int c_end = LSE ? BN / 32 : min(BN / 32, (N - n0 + 31) >> 5);
-            const uint32_t t_tile = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-            // the latencies of one chunk -- TMEM load, bias (LSE) / tanh' operand (aux) fetch -- are taken off the warp's
-            // critical path by fetching for the NEXT chunk while the current one is processed (two warps per scheduler
-            // cannot hide them: 24 % / 31 % of the epilogue's stall samples before this)
-            const bool aux_fast = !LSE && c_bf16 && lse.aux && full_m && ksplit == 1 && !accumulate;
-            auto aux_fetch = [&](const int c, uint2 (&hq)[8]) {
-                if (!(aux_fast && n0 + c * 32 + 32 <= N)) return;
-                const __nv_bfloat16* ap = lse.aux + (m0 + q * 32 + rsub) * N + (n0 + c * 32 + c4 * 4);
-#pragma unroll
-                for (int rr = 0; rr < 8; ++rr) hq[rr] = __ldg(reinterpret_cast<const uint2*>(ap + (long)(rr * 4) * N));
-            };
-            const bool bias_fast = LSE && bias && bias_vec;
-            float bq[32];                                        // LSE: bias of the chunk about to be processed
-            auto bias_fetch = [&](const int c) {
-                if (!(bias_fast && n0 + c * 32 + 32 <= N)) return;
-#pragma unroll
-                for (int i4 = 0; i4 < 8; ++i4) {
-                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n0 + c * 32 + i4 * 4));
-                    bq[i4 * 4] = b4.x; bq[i4 * 4 + 1] = b4.y; bq[i4 * 4 + 2] = b4.z; bq[i4 * 4 + 3] = b4.w;
-                }
-            };
-            uint2 ha[8], hb[8];
-            if (c_begin < c_end) { aux_fetch(c_begin, ha); if (LSE) bias_fetch(c_begin); }
             mbar_wait(tfull0 + 8 * acc, acc_phase);
             tc_fence_after();
-            auto process = [&](const int c, uint32_t (&r)[32], uint2 (&hq)[8], uint2 (&hq_next)[8]) {
+#pragma unroll 1
+            for (int c = (EPW_ == 8 ? chalf : 0); c < BN / 32; c += (EPW_ == 8 ? 2 : 1)) {
+                // a wide tile may hang over the last columns (N % 256 == 128): chunks past N are skipped, chunks
+                // inside keep the vector path
+                if (!LSE && n0 + c * 32 >= N) break;
                 const bool full = full_m && (n0 + c * 32 + 32 <= N);
-                if (c + CSTEP < c_end) aux_fetch(c + CSTEP, hq_next);
+                uint32_t r[32];
+                tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c * 32, r);
                 if (empty_split) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) r[i] = 0u;
@@ -306,17 +283,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     const int col0 = n0 + c * 32;
                     constexpr float LOG2E = 1.4426950408889634f;
                     float cm = -INFINITY;
-                    if (col0 + 32 <= N && bias_fast) {            // bias prefetched while the previous chunk was processed
-#pragma unroll
-                        for (int i4 = 0; i4 < 8; ++i4) {
-                            const float v0 = __uint_as_float(r[i4 * 4]) + bq[i4 * 4], v1 = __uint_as_float(r[i4 * 4 + 1]) + bq[i4 * 4 + 1];
-                            const float v2 = __uint_as_float(r[i4 * 4 + 2]) + bq[i4 * 4 + 2], v3 = __uint_as_float(r[i4 * 4 + 3]) + bq[i4 * 4 + 3];
-                            r[i4 * 4] = __float_as_uint(v0); r[i4 * 4 + 1] = __float_as_uint(v1);
-                            r[i4 * 4 + 2] = __float_as_uint(v2); r[i4 * 4 + 3] = __float_as_uint(v3);
-                            cm = fmaxf(fmaxf(cm, fmaxf(v0, v1)), fmaxf(v2, v3));
-                        }
-                        if (c + CSTEP < c_end) bias_fetch(c + CSTEP);
-                    } else if (col0 + 32 <= N && bias_vec) {      // whole chunk inside the vocabulary: no per-element guards
+                    if (col0 + 32 <= N && bias_vec) {             // whole chunk inside the vocabulary: no per-element guards
 #pragma unroll
                         for (int i4 = 0; i4 < 8; ++i4) {
                             const float4 b4 = bias ? __ldg(reinterpret_cast<const float4*>(bias + col0 + i4 * 4))
@@ -378,7 +345,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                                  : "=f"(vv[rr].x), "=f"(vv[rr].y), "=f"(vv[rr].z), "=f"(vv[rr].w)
                                  : "r"(sbuf + (uint32_t)((rr * 4 + rsub) * 36 + c4 * 4) * 4));
                 if (full && ksplit == 1 && !accumulate) {         // the common case, free of per-store mode tests
-                    if (c_bf16 && !LSE && lse.aux) {              // (== aux_fast here: hq was fetched one chunk ahead)
+                    if (c_bf16 && !LSE && lse.aux) {
+                        uint2 hq[8];
+#pragma unroll
+                        for (int rr = 0; rr < 8; ++rr)
+                            hq[rr] = __ldg(reinterpret_cast<const uint2*>(lse.aux + (row0 + rr * 4) * N + col));
 #pragma unroll
                         for (int rr = 0; rr < 8; ++rr) {
                             const float4 v = vv[rr];
@@ -468,20 +439,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     }
                 }
                 __syncwarp();
-            };
-            uint32_t ra[32], rb[32];
-            if (c_begin < c_end) tc_ld32_issue(t_tile + c_begin * 32, ra);
-#pragma unroll 1
-            for (int c = c_begin; c < c_end; c += 2 * CSTEP) {
-                tc_ld_wait(ra);
-                const bool more = c + CSTEP < c_end;
-                if (more) tc_ld32_issue(t_tile + (c + CSTEP) * 32, rb);
-                process(c, ra, ha, hb);
-                if (more) {
-                    tc_ld_wait(rb);
-                    if (c + 2 * CSTEP < c_end) tc_ld32_issue(t_tile + (c + 2 * CSTEP) * 32, ra);
-                    process(c + CSTEP, rb, hb, ha);
-                }
             }
             if (LSE && nb == num_n - 1) {                         // whole vocabulary seen: publish the row statistics
                 if (EPW_ == 8) {
