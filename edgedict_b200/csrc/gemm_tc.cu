@@ -484,6 +484,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
 }
 
+// split-K (weight gradients: few output tiles, contraction over up to millions of rows).  The persistent grid
+// processes tiles*ksplit work items in waves of one per worker (SM, or CTA pair); a ragged last wave idles most of
+// the machine (20 tiles x 15 splits = 300 items = 2.03 waves ran at 67 %), so ksplit is chosen to fill whole waves:
+// maximise  wave efficiency / (1 + r * ksplit / nkb):  items / (waves * workers) against the cost of one more
+// atomic tile epilogue per split, which was measured at r ~ 32 k-blocks of MMA time for the 128x256 tile
+// (lstm dW, 128 tiles, 500 k-blocks: ksplit 3 -> 228 us, 8 -> 254 us; joint dW2, 20 tiles, 32250 k-blocks:
+// ksplit 15 -> 3.7 ms, 22 -> 2.8 ms).  Partial tiles are reduced with fp32 atomics.
+int choose_ksplit(long out_tiles, long nkb, long workers, double r) {
+    int ksplit = 1;
+    long cap = nkb / 16;
+    if (cap > 64) cap = 64;
+    double best = -1.0;
+    for (long ks = 1; ks <= cap; ++ks) {
+        const long items = out_tiles * ks;
+        const long waves = (items + workers - 1) / workers;
+        const double score = (double)items / (double)(waves * workers) / (1.0 + r * (double)ks / (double)nkb);
+        if (score > best) { best = score; ksplit = (int)ks; }
+    }
+    return ksplit;
+}
+
 template <bool A_MN, bool B_MN, int BN_>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, void* C, int c_bf16, const float* bias, int accumulate,
            long M, int N, long K, cudaStream_t st, const void* aux = nullptr) {
@@ -492,27 +513,8 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, void* C, int c_bf16, co
     constexpr int BN = BN_;
     const long out_tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     const long nkb = (K + BK - 1) / BK;
-    // split-K (weight gradients: few output tiles, contraction over up to millions of rows).  The persistent grid
-    // processes tiles*ksplit work items in waves of one per SM; a ragged last wave idles most of the machine
-    // (20 tiles x 15 splits = 300 items = 2.03 waves ran at 67 %), so ksplit is chosen to fill whole waves:
-    // maximise  wave efficiency / (1 + r * ksplit / nkb):  items / (waves * SMs) against the cost of one more
-    // atomic tile epilogue per split, which was measured at r ~ 32 k-blocks of MMA time for the 128x256 tile
-    // (lstm dW, 128 tiles, 500 k-blocks: ksplit 3 -> 228 us, 8 -> 254 us; joint dW2, 20 tiles, 32250 k-blocks:
-    // ksplit 15 -> 3.7 ms, 22 -> 2.8 ms).  Partial tiles are reduced with fp32 atomics.
     int ksplit = 1;
-    if (!c_bf16 && nkb >= 64 && out_tiles < eb_num_sms()) {
-        const long S = eb_num_sms();
-        long cap = nkb / 16;
-        if (cap > 64) cap = 64;
-        const double r = BN == 256 ? 32.0 : 16.0;
-        double best = -1.0;
-        for (long ks = 1; ks <= cap; ++ks) {
-            const long items = out_tiles * ks;
-            const long waves = (items + S - 1) / S;
-            const double score = (double)items / (double)(waves * S) / (1.0 + r * (double)ks / (double)nkb);
-            if (score > best) { best = score; ksplit = (int)ks; }
-        }
-    }
+    if (!c_bf16 && nkb >= 64 && out_tiles < eb_num_sms()) ksplit = choose_ksplit(out_tiles, nkb, eb_num_sms(), BN == 256 ? 32.0 : 16.0);
     if (ksplit > 1 && !accumulate) EB_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, st));
     const long tiles = out_tiles * ksplit;
     const int grid = (int)(tiles < eb_num_sms() ? tiles : eb_num_sms());
@@ -566,11 +568,11 @@ int pair_mode() {
     return g_pair_mode;
 }
 
-template <bool B_MN, bool LSE>
+template <bool A_MN, bool B_MN, bool LSE>
 int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, void* C, int c_bf16, const float* bias, int accumulate,
                 long M, int N, long K, const LseArgs& ea, cudaStream_t st) {
     using C_ = Cfg<256, 8, false, true>;
-    auto kern = gemm_tc_kernel<false, B_MN, 256, LSE, 8, false, true>;
+    auto kern = gemm_tc_kernel<A_MN, B_MN, 256, LSE, 8, false, true>;
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
@@ -586,10 +588,14 @@ int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, void* C, int c_bf1
         if (n <= 0) return EB_ERR_CUDA;
         max_pairs = n < eb_num_sms() / 2 ? n : eb_num_sms() / 2;
     }
-    const long work = ((M + 255) / 256) * (LSE ? 1 : (N + 255) / 256);
+    const long out_tiles = ((M + 255) / 256) * ((N + 255) / 256), nkb = (K + BK - 1) / BK;
+    int ks1 = 1;                                             // split-K as in launch(), one work item per CTA pair
+    if (!LSE && !c_bf16 && nkb >= 64 && out_tiles < max_pairs) ks1 = choose_ksplit(out_tiles, nkb, max_pairs, 32.0);
+    if (ks1 > 1 && !accumulate) EB_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, st));
+    const long work = LSE ? (M + 255) / 256 : out_tiles * ks1;
     const int pairs = (int)(work < max_pairs ? work : max_pairs);
     cfg.gridDim = dim3(2 * pairs);
-    int c16 = c_bf16, acc = accumulate, ks1 = 1;
+    int c16 = c_bf16, acc = accumulate;
     EB_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, C, c16, bias, acc, M, N, K, ks1, ea));
     EB_CHECK_LAUNCH();
     return EB_OK;
@@ -630,10 +636,9 @@ EB_API int eb_joint_logits_lse(const void* hidden16, const void* w2_16, const fl
         return EB_ERR_INVALID;
     const long M = (long)B * maxT * maxU;
     const bool wide = (V % 256 == 0);
-    // cta_group::2 tiles only on request: measured at E6D2 (profiles/r2/prof_r2_gemm_pair.txt) they cut the L2 -> SM
-    // operand traffic by a third (15.9 -> 10.6 GB per launch) but not the time (1.35 vs 1.37-1.43 ms): with the epilogue
-    // switched off the mainloop alone runs at ~1400 TFLOP/s either way, the softmax epilogue's cost is added on top
-    const bool pair = wide && pair_mode() == 1;
+    // cta_group::2 tiles when there are enough 256-row blocks for every CTA pair: a third less L2 -> SM operand traffic
+    // (15.9 -> 10.6 GB per launch at E6D2, profiles/r2/prof_r2_gemm_pair.txt), 1.33 -> 1.25 ms alone, -0.3 ms per step
+    const bool pair = wide && (pair_mode() == 1 || (pair_mode() < 0 && (M + 255) / 256 >= 2L * (eb_num_sms() / 2)));
     CUtensorMap ta, tb;
     if (!make_map(&ta, hidden16, (uint64_t)J, (uint64_t)M, 128) ||
         !make_map(&tb, w2_16, (uint64_t)J, (uint64_t)V, (wide && !pair) ? 256 : 128)) {
@@ -644,7 +649,7 @@ EB_API int eb_joint_logits_lse(const void* hidden16, const void* w2_16, const fl
     lse.labels = labels; lse.xlen = xlen; lse.ylen = ylen; lse.denom = denom; lse.lpb = lpb; lse.lpl = lpl;
     lse.maxT = maxT; lse.maxU = maxU; lse.blank = blank;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (pair) return launch_pair<false, true>(ta, tb, logits16, 1, b2, 0, M, V, J, lse, st);
+    if (pair) return launch_pair<false, false, true>(ta, tb, logits16, 1, b2, 0, M, V, J, lse, st);
     return wide ? launch_lse<256>(ta, tb, logits16, b2, M, V, J, lse, st) : launch_lse<128>(ta, tb, logits16, b2, M, V, J, lse, st);
 }
 
@@ -700,12 +705,17 @@ static int gemm_dispatch(const void* A, int a_mn_major, const void* B, int b_mn_
     if (force_bn == 128) wide = false;
     if (force_bn == 256 && N % 128 == 0) wide = true;
     if (low) wide = false;
+    // split-K weight gradients with both operands MN-major take pair tiles only on request (mode 1): the joint's dW2
+    // (1024 x 640 over 1 M lattice cells) runs 1.42 -> 1.11 ms alone, but inside the step -- on the side stream, next to
+    // the d-hidden GEMM -- the same-box A/B showed no gain (47.95 vs 48.0 ms), and the LSTM weight gradients lose 0.3 ms
+    const bool wgrad_pair = !c_bf16 && a_mn_major && b_mn_major && !low && N % 128 == 0 && N >= 256 && M >= 256 &&
+                            pair_mode() == 1;
+    if (wgrad_pair) wide = true;
     if (pair_mode() == 1 && c_bf16 && !a_mn_major && !low && N % 128 == 0 && N >= 256) wide = true;   // (tests) any legal shape
-    // cta_group::2 pairs: bf16 outputs (no split-K), A K-major, wide tiles.  Automatic for the MN-major-B product with
-    // enough 256-row blocks for every pair -- the joint's d-hidden GEMM, 1.53 -> 1.38 ms at E6D2 -- and on request
-    // (mode 1) for any legal shape; the K-major-B products measured no faster (see eb_joint_logits_lse).
-    const bool pair = wide && c_bf16 && !a_mn_major &&
-                      (pair_mode() == 1 || (pair_mode() < 0 && b_mn_major && (M + 255) / 256 >= 2L * (eb_num_sms() / 2)));
+    // cta_group::2 pairs: bf16 outputs (no split-K), A K-major, wide tiles.  Automatic with enough 256-row blocks for
+    // every pair -- the joint's d-hidden GEMM, 1.53 -> 1.34 ms at E6D2 -- and on request (mode 1) for any legal shape.
+    const bool pair = wgrad_pair || (wide && c_bf16 && !a_mn_major &&
+                      (pair_mode() == 1 || (pair_mode() < 0 && (M + 255) / 256 >= 2L * (eb_num_sms() / 2))));
     CUtensorMap ta, tb;
     bool ok = a_mn_major ? make_map(&ta, A, (uint64_t)M, (uint64_t)K, 64) : make_map(&ta, A, (uint64_t)K, (uint64_t)M, 128);
     ok = ok && (b_mn_major ? make_map(&tb, B, (uint64_t)N, (uint64_t)K, 64)
@@ -719,8 +729,9 @@ static int gemm_dispatch(const void* A, int a_mn_major, const void* B, int b_mn_
     if (pair) {
         LseArgs ea = LseArgs();
         ea.aux = reinterpret_cast<const __nv_bfloat16*>(aux);
-        return b_mn_major ? launch_pair<true, false>(ta, tb, C, c_bf16, bias, accumulate, M, N, K, ea, st)
-                          : launch_pair<false, false>(ta, tb, C, c_bf16, bias, accumulate, M, N, K, ea, st);
+        if (a_mn_major) return launch_pair<true, true, false>(ta, tb, C, c_bf16, bias, accumulate, M, N, K, ea, st);
+        return b_mn_major ? launch_pair<false, true, false>(ta, tb, C, c_bf16, bias, accumulate, M, N, K, ea, st)
+                          : launch_pair<false, false, false>(ta, tb, C, c_bf16, bias, accumulate, M, N, K, ea, st);
     }
 #define EB_GO(AM, BMN)                                                                              \
     return wide ? launch<AM, BMN, 256>(ta, tb, C, c_bf16, bias, accumulate, M, N, K, st, aux)      \

@@ -64,10 +64,9 @@ int eb_gemm_bf16_ex(const void* A, int a_mn_major, const void* B, int b_mn_major
                     const float* bias, int accumulate, long M, int N, long K, int flags, void* stream);
 
 /* cta_group::2 tiles (two CTAs of a cluster share one 256 x 256 tile, each staging half of the B operand) for the
- * bf16-output GEMMs with K-major A -- the joint's logits (+LSE) and d-hidden products.  mode -1 = automatic (the MN-major-B
- * product with enough 256-row blocks for every CTA pair, i.e. d-hidden: the only one measured faster), 0 = never,
- * 1 = whenever legal; returns the previous mode.  The
- * default comes from EDGEDICT_GEMM_PAIR. */
+ * bf16-output GEMMs with K-major A -- the joint's logits (+LSE) and d-hidden products -- and, on request only, for
+ * split-K weight gradients with both operands MN-major.  mode -1 = automatic (bf16-output products with enough 256-row
+ * blocks for every CTA pair), 0 = never, 1 = whenever legal; returns the previous mode.  Default: EDGEDICT_GEMM_PAIR. */
 int eb_gemm_pair_mode(int mode);
 
 /* C16[M,N] = bf16((A B) * (1 - hid16[M,N]^2)): the joint's d-hidden GEMM with the derivative of Joint.forward's Tanh

@@ -60,6 +60,19 @@ def check():
         print("nn' M=%d N=%d K=%d: pair vs torch %.2e, bit-identical: %s" % (M, N, K, e, same))
         assert e < 1e-2 and same
         worst = max(worst, e)
+    # split-K weight gradient, both operands MN-major (dW2 = dlogits^T hid): fp32 atomics, so not bit-identical
+    for (M, N, K) in [(1024, 640, 64 * 700 + 24), (512, 256, 64 * 130), (320, 384, 64 * 97)]:
+        dy = (torch.randn(K, M, device=dev) * 0.1).to(bf16)
+        x = torch.randn(K, N, device=dev).to(bf16)
+        ref, got = both(lambda: ops.gemm_bf16(dy, 1, x, 1, M, N, K))
+        want = dy.float().t() @ x.float()
+        e0 = float((ref - want).abs().max() / want.abs().max())
+        e1 = float((got - want).abs().max() / want.abs().max())
+        print("tn  M=%d N=%d K=%d: one-CTA vs torch %.2e, pair vs torch %.2e" % (M, N, K, e0, e1))
+        assert e1 < 2e-5
+        acc0 = torch.randn(M, N, device=dev)
+        ref, got = both(lambda: ops.gemm_bf16(dy, 1, x, 1, M, N, K, out=acc0.clone(), accumulate=True))
+        assert float((got - (want + acc0)).abs().max() / want.abs().max()) < 2e-5
     # logits + LSE: ragged lattice, V = 512 and 1024
     for (B, T, U, V, J) in [(3, 37, 9, 512, 128), (2, 150, 33, 1024, 640), (5, 41, 7, 256, 64)]:
         hid = torch.tanh(torch.randn(B, T, U, J, device=dev)).to(bf16)
@@ -107,9 +120,10 @@ def time_(once=False):
         ops.gemm_pair_mode(mode)
         t1 = ev_time(lambda: ops.joint_logits_lse(hid, w2, b2, labels, xlen, ylen, B, T, U, 0))
         t2 = ev_time(lambda: ops.gemm_bf16_dtanh(dlog, w2, 1, hid.view(M, J), M, J, V))
+        t3 = ev_time(lambda: ops.gemm_bf16(dlog, 1, hid.view(M, J), 1, V, J, M))
         fl = 2.0 * M * V * J
-        print("pair_mode %d: logits+LSE %.3f ms (%.0f TFLOP/s)   d-hidden(tanh') %.3f ms (%.0f TFLOP/s)"
-              % (mode, t1, fl / t1 / 1e9, t2, fl / t2 / 1e9))
+        print("pair_mode %d: logits+LSE %.3f ms (%.0f TFLOP/s)   d-hidden(tanh') %.3f ms (%.0f TFLOP/s)   dW2 %.3f ms (%.0f TFLOP/s)"
+              % (mode, t1, fl / t1 / 1e9, t2, fl / t2 / 1e9, t3, fl / t3 / 1e9))
     ops.gemm_pair_mode(-1)
 
 

@@ -122,6 +122,12 @@ def test_gemm_bf16_cta_pair_tiles_match_one_cta_tiles():
         one, two = both(lambda: ops.gemm_bf16_dtanh(A, Wn, True, hid, M, N, K))
         assert torch.equal(one, two)
         assert rel_err(two.float().cpu(), ((A.float() @ Wn.float()) * (1 - hid.float() ** 2)).cpu()) < 1e-2
+    # split-K weight gradient, both operands MN-major (fp32 atomics: compared with the fp32 product, not bit for bit)
+    for (M, N, K) in [(1024, 640, 64 * 700 + 24), (320, 384, 64 * 97)]:
+        dy, x = (rn(K, M) * 0.1).bfloat16(), rn(K, N).bfloat16()
+        one, two = both(lambda: ops.gemm_bf16(dy, 1, x, 1, M, N, K))
+        want = dy.float().t() @ x.float()
+        assert rel_err(two.cpu(), want.cpu()) < 2e-5 and rel_err(one.cpu(), want.cpu()) < 2e-5
     for (B, T, U, V, J) in [(3, 37, 9, 512, 128), (2, 150, 33, 1024, 640)]:
         hid, w2, b2 = torch.tanh(rn(B, T, U, J)).bfloat16(), (rn(V, J) * 0.2).bfloat16(), rn(V)
         labels = torch.randint(1, V, (B, U - 1), dtype=torch.int32, device="cuda", generator=g)
