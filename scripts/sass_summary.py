@@ -1,11 +1,11 @@
 """Per-kernel SASS mnemonic counts of libedgedict_b200.so (cuobjdump -sass): which kernels carry tcgen05 (UTCHMMA / UTCQMMA),
 TMA (UTMALDG / UTMASTG), bulk DSMEM copies (UBLKCP), TMEM loads (LDTM), legacy tensor-core MMAs (HMMA), cp.async (LDGSTS),
-cluster barriers (UCGABAR) and mbarrier waits (SYNCS).  Writes profiles/r2/sass_summary.txt."""
+cluster barriers (UCGABAR), mbarrier waits (SYNCS) and cta_group::2 forms (any mnemonic carrying .2CTA).  Writes profiles/r2/sass_summary.txt."""
 import collections, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = os.path.join(ROOT, "edgedict_b200", "libedgedict_b200.so")
 out = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
-KEYS = ["UTCHMMA", "UTCQMMA", "UTMALDG", "UTMASTG", "UBLKCP", "LDTM", "STTM", "UTCBAR", "HMMA", "LDGSTS", "LDSM", "UCGABAR", "SYNCS", "MEMBAR", "ATOMG", "RED"]
+KEYS = ["UTCHMMA", "UTCQMMA", "UTMALDG", "UTMASTG", "UBLKCP", "LDTM", "STTM", "UTCBAR", "HMMA", "LDGSTS", "LDSM", "UCGABAR", "SYNCS", "MEMBAR", "ATOMG", "RED", "2CTA"]
 rows, cur = collections.OrderedDict(), None
 for line in out.splitlines():
     m = re.search(r"Function : (\S+)", line)
@@ -23,6 +23,8 @@ for line in out.splitlines():
         for k in KEYS:
             if op.startswith(k):
                 rows[cur][k] += 1
+        if ".2CTA" in op:
+            rows[cur]["2CTA"] += 1
         rows[cur]["_total"] += 1
 os.makedirs(os.path.join(ROOT, "profiles", "r2"), exist_ok=True)
 with open(os.path.join(ROOT, "profiles", "r2", "sass_summary.txt"), "w") as fh:
