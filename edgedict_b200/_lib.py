@@ -34,6 +34,7 @@ SIGNATURES = {
     "eb_lstm_tc_set_trace": (I, [P, I]),
     "eb_lstm_tc_fwd": (I, [P, P, P, P, P, P, P, P, P, P, P, I, I, I, P]),
     "eb_lstm_tc_bwd": (I, [P, P, P, P, P, P, P, P, P, P, P, I, I, I, P]),
+    "eb_lstm_tc_bwd_chunks": (I, [P, P, P, P, P, P, P, P, P, P, P, I, P, I, I, P]),
     "eb_lstm_c4_supported": (I, [I, I]),
     "eb_lstm_c4_bwd_cluster": (I, [I]),
     "eb_lstm_c4_max_clusters": (I, [I, I]),

@@ -294,6 +294,10 @@ struct BwdP {
     float* pglob;                 // [H/(8*CS)][CS][8*CS][NB] partial tiles in L2 (non-cluster variant)
     long long* trace; int trace_steps;   // debug: clock64 stamps of CTA 0 (eb_lstm_tc_set_trace)
     int B, T, H;
+    // time axis in segments (chunk-major storage of the layer wavefront, functional._Chunks): segment c covers steps
+    // [seg_off[c], seg_off[c+1]) and is a contiguous [Btot, len_c, D] block at row Btot * seg_off[c]; one segment = [B,T,D]
+    int b0, Btot, nseg;
+    int seg_off[9];
 };
 #define TC_STAMP(step, s)                                                                          \
     do {                                                                                           \
@@ -337,6 +341,12 @@ __global__ void __launch_bounds__(NW * 32, 1) lstm_tc_bwd_kernel(BwdP p) {
     const int ks0 = w * ksper;
     const int myks = max(0, min(ksper, nks - ks0));
     const size_t xstride = (size_t)NB * H4;
+    auto rowof = [&](int b, int t) -> long {                 // row of (batch b of this tile, step t) in the saved tensors
+        int c = 0;
+        while (c + 1 < p.nseg && t >= p.seg_off[c + 1]) ++c;
+        const int lo = p.seg_off[c];
+        return (long)p.Btot * lo + (long)(p.b0 + b) * (p.seg_off[c + 1] - lo) + (t - lo);
+    };
 
     // The contraction index is ordered unit-major, r' = 4*j + g, so that a K-slice is produced by a
     // contiguous range of CTAs (8 units x 4 gates each):  A(m = unit u, k = r') = W_hh[g*H + j, u]
@@ -389,11 +399,11 @@ __global__ void __launch_bounds__(NW * 32, 1) lstm_tc_bwd_kernel(BwdP p) {
     float in4 = 0.f, in5 = 0.f, in6 = 0.f;
 #define EB_PREFETCH(tt)                                                                                   \
     if (own && (tt) >= 0) {                                                                               \
-        const long bt_ = (long)bb * T + (tt);                                                             \
+        const long bt_ = rowof(bb, (tt));                                                                 \
         const float* gp_ = p.gates + bt_ * H4 + j;                                                        \
         _Pragma("unroll") for (int g_ = 0; g_ < 4; ++g_) cp_async4(pgs + g_ * (NW * 32), gp_ + (long)g_ * H); \
         in4 = __ldg(p.cseq + bt_ * H + j);                                                                \
-        in5 = ((tt) > 0) ? __ldg(p.cseq + (bt_ - 1) * H + j) : (p.c0 ? p.c0[(long)bb * H + j] : 0.f);     \
+        in5 = ((tt) > 0) ? __ldg(p.cseq + rowof(bb, (tt) - 1) * H + j) : (p.c0 ? p.c0[(long)bb * H + j] : 0.f); \
         in6 = __ldg(p.dy + bt_ * H + j);                                                                  \
     }
     EB_PREFETCH(T - 1)
@@ -438,7 +448,7 @@ __global__ void __launch_bounds__(NW * 32, 1) lstm_tc_bwd_kernel(BwdP p) {
         if (tid < NB * 4) {   // off the critical path: dG_t in the standard gate-major layout, 16-byte stores
             const int b = tid >> 2, c = tid & 3;
             const int jb = js * JS + rs * UPC;
-            if (b < B) *reinterpret_cast<uint4*>(p.dg16 + ((size_t)b * T + t) * H4 + (size_t)c * H + jb) =
+            if (b < B) *reinterpret_cast<uint4*>(p.dg16 + (size_t)rowof(b, t) * H4 + (size_t)c * H + jb) =
                 *reinterpret_cast<const uint4*>(sg + (b * 4 + c) * UPC);
         }
         EB_PREFETCH(t - 1)                                   // overlaps the wait
@@ -679,10 +689,38 @@ EB_API int eb_lstm_tc_fwd(const float* xg, const void* whh16, const float* h0, c
     return EB_OK;
 }
 
+static int tc_bwd_impl(const float* dy, const float* gates, const float* cseq, const float* c0,
+                       const void* whhT16, const float* dhT, const float* dcT, void* dg16, float* dh0,
+                       float* dc0, void* scratch, int B, int T, int H, const int* lens, int nseg, void* stream);
+
 // whhT16 [H,4H] bf16 (W_hh transposed).  dg16 [B,T,4H] bf16 out; dh0/dc0 [B,H] fp32 out.
 EB_API int eb_lstm_tc_bwd(const float* dy, const float* gates, const float* cseq, const float* c0,
                           const void* whhT16, const float* dhT, const float* dcT, void* dg16, float* dh0,
                           float* dc0, void* scratch, int B, int T, int H, void* stream) {
+    return tc_bwd_impl(dy, gates, cseq, c0, whhT16, dhT, dcT, dg16, dh0, dc0, scratch, B, T, H, &T, 1, stream);
+}
+
+// The same recurrence over a time axis stored chunk-major (the layer wavefront's buffers): chunk c, chunk_lens[c] steps,
+// is a contiguous [B, chunk_lens[c], D] block and the blocks follow each other -- ONE launch walks all chunks (T = their
+// sum) instead of one launch per chunk with the (dh, dc) carry through memory.  nchunks <= 8; chunk_lens is a host array.
+EB_API int eb_lstm_tc_bwd_chunks(const float* dy, const float* gates, const float* cseq, const float* c0,
+                                 const void* whhT16, const float* dhT, const float* dcT, void* dg16, float* dh0,
+                                 float* dc0, void* scratch, int B, const int* chunk_lens, int nchunks, int H,
+                                 void* stream) {
+    if (!chunk_lens || nchunks < 1 || nchunks > 8) return EB_ERR_INVALID;
+    long T = 0;
+    for (int c = 0; c < nchunks; ++c) {
+        if (chunk_lens[c] <= 0) return EB_ERR_INVALID;
+        T += chunk_lens[c];
+    }
+    if (T > 0x7fffffffL) return EB_ERR_INVALID;
+    return tc_bwd_impl(dy, gates, cseq, c0, whhT16, dhT, dcT, dg16, dh0, dc0, scratch, B, (int)T, H, chunk_lens, nchunks,
+                       stream);
+}
+
+static int tc_bwd_impl(const float* dy, const float* gates, const float* cseq, const float* c0,
+                       const void* whhT16, const float* dhT, const float* dcT, void* dg16, float* dh0,
+                       float* dc0, void* scratch, int B, int T, int H, const int* lens, int nseg, void* stream) {
     if (!dy || !gates || !cseq || !whhT16 || !dg16 || !dh0 || !dc0 || !scratch || T <= 0 || !tc_ok(B, H))
         return EB_ERR_INVALID;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -691,14 +729,15 @@ EB_API int eb_lstm_tc_bwd(const float* dy, const float* gates, const float* cseq
     for (int b0 = 0; b0 < B; b0 += NB) {
         const int nb = (B - b0 < NB) ? (B - b0) : NB;
         BwdP p;
-        p.dy = dy + (size_t)b0 * T * H;
-        p.gates = gates + (size_t)b0 * T * 4 * H;
-        p.cseq = cseq + (size_t)b0 * T * H;
+        p.dy = dy; p.gates = gates; p.cseq = cseq;           // batch tile and time segments are applied by rowof()
+        p.b0 = b0; p.Btot = B; p.nseg = nseg;
+        p.seg_off[0] = 0;
+        for (int c = 0; c < 8; ++c) p.seg_off[c + 1] = c < nseg ? p.seg_off[c] + lens[c] : T;
         p.c0 = c0 ? c0 + (size_t)b0 * H : nullptr;
         p.whhT = reinterpret_cast<const __nv_bfloat16*>(whhT16);
         p.dhT = dhT ? dhT + (size_t)b0 * H : nullptr;
         p.dcT = dcT ? dcT + (size_t)b0 * H : nullptr;
-        p.dg16 = reinterpret_cast<__nv_bfloat16*>(dg16) + (size_t)b0 * T * 4 * H;
+        p.dg16 = reinterpret_cast<__nv_bfloat16*>(dg16);
         p.dh0 = dh0 + (size_t)b0 * H;
         p.dc0 = dc0 + (size_t)b0 * H;
         p.bar = reinterpret_cast<unsigned*>(base);

@@ -263,6 +263,9 @@ class _Chunks:
         return out
 
 
+BPTT_ONE_LAUNCH = __import__("os").environ.get("EDGEDICT_BPTT_ONE_LAUNCH", "1") != "0"   # one BPTT launch per layer (else per chunk)
+
+
 class LSTMStack(torch.autograd.Function):
     """ResLayerNormLSTM.forward (rnnt/models.py:57-75) for all layers at once, bf16 tensor-core mode, zero
     initial state: per layer nn.LSTM -> LayerNorm(y + x) (no residual for layer 0) -> optional TimeReduction,
@@ -426,7 +429,10 @@ class LSTMStack(torch.autograd.Function):
                                                 out=k.blk(dg16, c))
             else:
                 hprev = y16[l] if c4 else k.new(H, bf16, dev)  # c4 forward: h_{t-1} already written by the kernel
-                for c in range(C - 1, -1, -1):
+                one_launch = c4 and BPTT_ONE_LAUNCH and C <= 8
+                if one_launch:                                 # the kernel walks the chunk-major buffers itself
+                    ops.lstm_tc_bwd_chunks(dz, gates[l], cseq[l], whhT16, k.lens, B, dg16)
+                for c in (() if one_launch else range(C - 1, -1, -1)):
                     _, dh, dc = ops.lstm_tc_bwd(k.blk(dz, c), k.blk(gates[l], c), k.blk(cseq[l], c),
                                                 cT[l, c - 1] if c else None, whhT16, dh, dc, out=k.blk(dg16, c))
                     if c4:

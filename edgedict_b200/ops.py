@@ -340,6 +340,22 @@ def lstm_tc_bwd(dy, gates, cseq, c0, whhT16, dhT, dcT, out=None):
     return dg16, dh0, dc0
 
 
+def lstm_tc_bwd_chunks(dy, gates, cseq, whhT16, lens, B, out):
+    """BPTT of one layer over chunk-major buffers (functional._Chunks: rows = B * sum(lens)) in ONE launch; zero initial and
+    final-state gradients.  dy [rows,H] fp32, gates [rows,4H], cseq [rows,H], out = dg16 [rows,4H] bf16."""
+    import ctypes
+    H = dy.shape[1]
+    dev = dy.device
+    dh0 = torch.empty(B, H, dtype=f32, device=dev)
+    dc0 = torch.empty(B, H, dtype=f32, device=dev)
+    arr = (ctypes.c_int * len(lens))(*[int(n) for n in lens])
+    with _timed("lstm_tc_bwd", 1, 0.0, 2.0 * B * sum(lens) * 4 * H * H):
+        check(lib().eb_lstm_tc_bwd_chunks(_p(dy), _p(gates), _p(cseq), None, _p(whhT16), None, None, _p(out), _p(dh0),
+                                          _p(dc0), _p(_lstm_tc_scratch(B, H, dev)), B, arr, len(lens), H, _s()),
+              "eb_lstm_tc_bwd_chunks")
+    return out, dh0, dc0
+
+
 # ---- cluster / tcgen05 recurrent kernels (csrc/lstm_c4.cu) ------------------------------------------
 _c4_ok = {}
 

@@ -293,11 +293,11 @@ class Transducer(nn.Module):
             h_dec, _ = self.decoder(ys)
         if not self.output_loss:
             return self.joint(h_enc, h_dec)
-        xl = scale_length(h_enc.shape[1], xlen).to(device=h_enc.device)
+        xl = _lens_to_device(_i32(scale_length(h_enc.shape[1], xlen)), h_enc.device)
+        yl = _lens_to_device(_i32(ylen), h_enc.device)
         l0, l2 = self.joint.joint[0], self.joint.joint[2]
         loss, costs = Fn.JointLoss.apply(h_enc, h_dec, l0.weight, l0.bias, l2.weight, l2.bias,
-                                         _i32(ys), _i32(xl), _i32(ylen.to(h_enc.device)), self.blank,
-                                         _precision(self))
+                                         _i32(ys), xl, yl, self.blank, _precision(self))
         self.last_costs = costs
         return loss
 
@@ -379,6 +379,17 @@ class Transducer(nn.Module):
 
 def _i32(t):
     return t.to(torch.int32).contiguous()
+
+
+def _lens_to_device(t, device):
+    """Host length vector -> device without stalling the host: a copy from PAGEABLE memory synchronises the stream first
+    (the host then sits behind the whole encoder forward, 0.2 - 0.4 ms of idle GPU per step in the kernel timeline); a pinned
+    staging tensor + non_blocking copy does not (the caching host allocator keeps the block until the copy has run)."""
+    if t.device == device or device.type != "cuda":
+        return t.to(device)
+    staged = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    staged.copy_(t)
+    return staged.to(device, non_blocking=True)
 
 
 def scale_length(T_out, xlen):

@@ -109,6 +109,12 @@ int eb_lstm_tc_fwd(const float* xg, const void* whh16, const float* h0, const fl
 int eb_lstm_tc_bwd(const float* dy, const float* gates, const float* cseq, const float* c0,
                    const void* whhT16, const float* dhT, const float* dcT, void* dg16, float* dh0, float* dc0,
                    void* scratch, int B, int T, int H, void* stream);
+/* eb_lstm_tc_bwd over a time axis stored chunk-major (functional.LSTMStack's wavefront buffers): chunk c is a contiguous
+ * [B, chunk_lens[c], D] block, the blocks follow each other; one launch walks all chunks (T = sum of chunk_lens,
+ * nchunks <= 8, chunk_lens a HOST array) instead of one launch per chunk with the (dh, dc) carry through memory. */
+int eb_lstm_tc_bwd_chunks(const float* dy, const float* gates, const float* cseq, const float* c0,
+                          const void* whhT16, const float* dhT, const float* dcT, void* dg16, float* dh0, float* dc0,
+                          void* scratch, int B, const int* chunk_lens, int nchunks, int H, void* stream);
 
 /* ---- LSTM layer on tcgen05 tensor cores inside thread-block clusters (bf16 mode; H % 256 == 0, H <= 1024) ----
  * csrc/lstm_c4.cu: W_hh slices resident in shared memory, h / dG exchanged through L2 with TMA pulls, partial gate

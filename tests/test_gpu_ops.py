@@ -291,6 +291,33 @@ def test_lstm_tensor_core_layer_vs_oracle(B, T, I, H):
         assert rel_err(a.grad.cpu(), r.grad) < 5e-2, name
 
 
+@pytest.mark.parametrize("B,H,lens", [(32, 256, [5, 5, 3]), (7, 1024, [4, 2]), (40, 128, [3, 3, 3, 1]), (32, 512, [6])])
+def test_lstm_bptt_one_launch_over_chunk_major_buffers(B, H, lens):
+    """eb_lstm_tc_bwd_chunks (one launch walking the wavefront's chunk-major buffers) == eb_lstm_tc_bwd once per chunk with
+    the (dh, dc) carry, bit for bit: same kernel, same arithmetic, only the row addressing differs.  B = 40 crosses the
+    32-row batch tile."""
+    from edgedict_b200 import ops
+    from edgedict_b200.functional import _Chunks
+    g = torch.Generator(device="cuda").manual_seed(3)
+    rn = lambda *s: torch.randn(*s, device="cuda", generator=g)
+    k = _Chunks(B, lens)
+    T = sum(lens)
+    whhT16 = (rn(H, 4 * H) / np.sqrt(H)).bfloat16()
+    gates = torch.sigmoid(rn(k.rows, 4 * H))
+    gates[:, 2 * H:3 * H] = torch.tanh(rn(k.rows, H))                  # the cell candidate is a tanh
+    cseq, dy = rn(k.rows, H), rn(k.rows, H)
+    one = torch.full((k.rows + 1, 4 * H), 7.0, device="cuda").bfloat16()
+    _, dh1, dc1 = ops.lstm_tc_bwd_chunks(dy, gates, cseq, whhT16, lens, B, one[:k.rows])
+    ref = torch.empty(k.rows, 4 * H, device="cuda").bfloat16()
+    dh = dc = None
+    for c in range(len(lens) - 1, -1, -1):
+        c_prev = k.blk(cseq, c - 1)[:, -1].contiguous() if c else None
+        _, dh, dc = ops.lstm_tc_bwd(k.blk(dy, c), k.blk(gates, c), k.blk(cseq, c), c_prev, whhT16, dh, dc, out=k.blk(ref, c))
+    torch.cuda.synchronize()
+    assert torch.equal(one[:k.rows], ref) and (one[k.rows] == 7.0).all()
+    assert torch.equal(dh1, dh) and torch.equal(dc1, dc)
+
+
 @pytest.mark.parametrize("M,N,K", [(300, 128, 64), (1000, 640, 256), (257, 72, 96)])
 def test_gemm_dtanh_epilogue_and_dpre_reductions(M, N, K):
     """eb_gemm_bf16_dtanh: (A B) * (1 - hid^2) in the GEMM epilogue (full and edge tiles), then eb_joint_dpre_reduce."""
