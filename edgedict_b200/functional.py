@@ -484,20 +484,41 @@ def _joint_pre(h_enc, h_dec, w1, b1, precision):
     return he2, hd2, ep, dp
 
 
+JOINT_WGRAD_SIDE = __import__("os").environ.get("EDGEDICT_JOINT_WGRAD_SIDE", "1") != "0"
+
+
 def _joint_bwd(ctx_p, dlog2, hid, he2, hd2, w1, w2, dims, db2=None):
     """Shared backward of the joint given d logits [N_cells, V] (fp32 or bf16); db2 may already have
     been accumulated by the fused loss-gradient kernel."""
     B, T, U, E, Dd, J, V = dims
     p = ctx_p
     dl16 = dlog2 if dlog2.dtype == bf16 else (ops.cast_bf16(dlog2) if p == "bf16" else None)
-    if db2 is None:
-        db2 = ops.colsum(dlog2)
     hid2 = hid.view(B * T * U, J)
-    if p == "bf16" and V % 256 == 0:
-        # compute dW2^T = hidden^T dlogits ([J, V]: 256-wide tcgen05 tiles divide V, not J) and flip it
-        dw2 = ops.mm_tn(hid2, dl16, p, dy16=hid2, x16=dl16).t().contiguous()
+
+    def out_layer_grads(db2):
+        if db2 is None:
+            db2 = ops.colsum(dlog2)
+        if p == "bf16" and V % 256 == 0:
+            # compute dW2^T = hidden^T dlogits ([J, V]: 256-wide tcgen05 tiles divide V, not J) and flip it
+            dw2 = ops.mm_tn(hid2, dl16, p, dy16=hid2, x16=dl16).t().contiguous()
+        else:
+            dw2 = ops.mm_tn(dlog2, hid2, p, dy16=dl16, x16=hid2 if p == "bf16" else None)
+        return dw2, db2
+
+    side = None
+    if JOINT_WGRAD_SIDE and p == "bf16" and dlog2.is_cuda:
+        # the output layer's weight / bias gradients (a 4.2 GB column sum + the split-K dW2 GEMM, 2.5 ms at E6D2) are off
+        # the critical path to the encoder: they run on a side stream under the d-hidden GEMM and the two d-pre reductions
+        main = torch.cuda.current_stream(dlog2.device)
+        side = _side_streams(dlog2.device)[1]
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            dw2, db2 = out_layer_grads(db2)
+        for t_ in (dlog2, dl16, hid2):
+            if t_ is not None:
+                t_.record_stream(side)
     else:
-        dw2 = ops.mm_tn(dlog2, hid2, p, dy16=dl16, x16=hid2 if p == "bf16" else None)
+        dw2, db2 = out_layer_grads(db2)
     if p == "bf16" and J % 8 == 0 and hid.dtype == bf16:
         # tanh' applied in the d-hidden GEMM's epilogue: d(pre-activation) leaves the GEMM, then two pure reductions
         dpre = ops.gemm_bf16_dtanh(dl16, ops.cast_bf16(w2.contiguous()), True, hid2, B * T * U, J, V)
@@ -513,6 +534,10 @@ def _joint_bwd(ctx_p, dlog2, hid, he2, hd2, w1, w2, dims, db2=None):
     dw1[:, :E] = ops.mm_tn(dep2, he2, p)
     dw1[:, E:] = ops.mm_tn(ddp2, hd2, p)
     db1 = ops.colsum(dep2)
+    if side is not None:
+        main.wait_stream(side)
+        dw2.record_stream(main)
+        db2.record_stream(main)
     return dhe, dhd, dw1, db1, dw2, db2
 
 
