@@ -318,6 +318,18 @@ def test_lstm_bptt_one_launch_over_chunk_major_buffers(B, H, lens):
     assert torch.equal(dh1, dh) and torch.equal(dc1, dc)
 
 
+@pytest.mark.parametrize("B,T,U,J", [(3, 70, 9, 640), (2, 33, 129, 72), (5, 32, 4, 128), (1, 250, 17, 320)])
+def test_joint_dpre_reduce_shapes(B, T, U, J):
+    """eb_joint_dpre_reduce (dep = sum over u, ddp = sum over t of the bf16 d-pre-activation) vs torch in fp64 at shapes
+    with many frames / ragged column counts."""
+    from edgedict_b200 import ops
+    d = _r(B, T, U, J, seed=21).bfloat16().cuda()
+    dep, ddp = ops.joint_dpre_reduce(d)
+    ref = d.double().cpu()
+    assert rel_err(dep.cpu(), ref.sum(2)) < 1e-5
+    assert rel_err(ddp.cpu(), ref.sum(1)) < 1e-5
+
+
 @pytest.mark.parametrize("M,N,K", [(300, 128, 64), (1000, 640, 256), (257, 72, 96)])
 def test_gemm_dtanh_epilogue_and_dpre_reductions(M, N, K):
     """eb_gemm_bf16_dtanh: (A B) * (1 - hid^2) in the GEMM epilogue (full and edge tiles), then eb_joint_dpre_reduce."""
