@@ -128,6 +128,8 @@ struct C4FwdP {
     long long* trace;             // debug: [steps][16] clock64 stamps of CTA 0 (eb_lstm_c4_set_trace), else null
     int trace_steps;
     float* gates_std; float* cseq_std;   // optional saves in the layout of eb_lstm_tc_bwd: [B,T,4H] gates, [B,T,H] cells (fp32)
+    int wpoll;                    // every warp polls the barrier counter itself instead of one poller + block barrier (default;
+                                  // EDGEDICT_LSTM_WPOLL bit 0 = this kernel, bit 1 = the BPTT kernel: -0.15 / -1.05 ms per step)
     int B, T, H;
 };
 
@@ -250,8 +252,13 @@ __global__ void __launch_bounds__(NGT, 2) lstm_c4_fwd_kernel(C4FwdP p) {
     for (int t = 0; t < T; ++t) {
         const uint32_t ph = (uint32_t)(t & 1);
         // ---- grid barrier: every CTA has published h_{t-1}; one poller, then the block
-        if (tid == 0) spin_wait_ge(wait_ctr, (unsigned)(t + 1) * nprod);   // (a back-off between polls changes nothing: measured)
-        __syncthreads();
+        if (p.wpoll) {
+            if (lane == 0) spin_wait_ge(wait_ctr, (unsigned)(t + 1) * nprod);
+            __syncwarp();
+        } else {
+            if (tid == 0) spin_wait_ge(wait_ctr, (unsigned)(t + 1) * nprod);   // (a back-off between polls changes nothing: measured)
+            __syncthreads();
+        }
         if (tid == 0) C4_STAMP(t, 0);
         // ---- A. pull this CTA's K slice of h_{t-1} (L2 -> swizzled shared tile)
         if (NACC == 4) {
@@ -807,6 +814,7 @@ EB_API int eb_lstm_c4_fwd(const float* xg, const void* whh16, const float* h0, c
         p.B = (B - b0 < NB) ? (B - b0) : NB; p.T = T; p.H = H;
         p.trace = g_trace; p.trace_steps = g_trace_steps;
         p.gates_std = gates_std ? gates_std + (size_t)b0 * T * 4 * H : nullptr;
+        { static int wp = -1; if (wp < 0) { const char* e = getenv("EDGEDICT_LSTM_WPOLL"); wp = e ? atoi(e) : 3; } p.wpoll = wp & 1; }
         p.cseq_std = cseq_std ? cseq_std + (size_t)b0 * T * H : nullptr;
         EB_CUDA(cudaMemsetAsync(scratch, 0, C4_HDR, st));
         bool ok = false;
