@@ -142,8 +142,11 @@ __device__ __forceinline__ void cp_async16(uint32_t saddr, const void* gmem) {
 // co-resident CTAs shared that bandwidth) and the CTA's shared-memory footprint drops from 111 KB to 46 KB.
 // NACC: independent accumulators (k step j goes to accumulator j % NACC, summed by the epilogue): back-to-back tcgen05.mma
 // into ONE accumulator with N = 32 run at ~75 cycles each whatever the operand source -- a dependent chain, not a bandwidth limit.
-template <bool TA, int NACC>
-__global__ void __launch_bounds__(NGT, 2) lstm_c4_fwd_kernel(C4FwdP p) {
+// MINB: register budget as CTAs per SM (2 -> 255, 3 -> 168, 4 -> 128 registers per thread).  Two of these CTAs share an SM in the
+// layer wavefront; at 232 registers they left 6 K of the SM's 64 K registers, so that neither the LayerNorm nor anything else of
+// the wavefront could run beside them; 168 registers cost 8 bytes more stack (EDGEDICT_C4_MINB).
+template <bool TA, int NACC, int MINB = 3>
+__global__ void __launch_bounds__(NGT, MINB) lstm_c4_fwd_kernel(C4FwdP p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int H = p.H, B = p.B, T = p.T;
@@ -714,6 +717,12 @@ int bwd_cs(int H) {
     return c;
 }
 
+inline int fwd_minb() {             // register budget of the default variant (TA, 4 accumulators): EDGEDICT_C4_MINB = 2 | 3 | 4
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("EDGEDICT_C4_MINB"); v = e ? atoi(e) : 3; if (v < 2 || v > 4) v = 3; }
+    return v;
+}
+
 // the forward kernel variant selected by the environment (TA x NACC)
 #define C4_FWD_DISPATCH(EXPR)                                                                        \
     do {                                                                                             \
@@ -721,6 +730,8 @@ int bwd_cs(int H) {
         if (fwd_tmem_a()) {                                                                          \
             if (n_ == 1) { auto kern = lstm_c4_fwd_kernel<true, 1>; EXPR; }                          \
             else if (n_ == 2) { auto kern = lstm_c4_fwd_kernel<true, 2>; EXPR; }                     \
+            else if (fwd_minb() == 2) { auto kern = lstm_c4_fwd_kernel<true, 4, 2>; EXPR; }          \
+            else if (fwd_minb() == 4) { auto kern = lstm_c4_fwd_kernel<true, 4, 4>; EXPR; }          \
             else { auto kern = lstm_c4_fwd_kernel<true, 4>; EXPR; }                                  \
         } else {                                                                                     \
             if (n_ == 1) { auto kern = lstm_c4_fwd_kernel<false, 1>; EXPR; }                         \
