@@ -7,7 +7,8 @@
 //   joint logits            logits = tanh(.) * W2^T  (rnnt/models.py:165, 2.7 TFLOP at E6D2)
 //   and their dgrad / wgrad counterparts (operands read MN-major, no transposes materialised).
 //
-// Kernel anatomy (one CTA per SM, persistent over output tiles of 128 x 128, BK = 64):
+// Kernel anatomy (one CTA per SM, persistent over output tiles of 128 x 128 / 128 x 256 -- or one CTA PAIR per 256 x 256 tile
+// with tcgen05.mma.cta_group::2, see Cfg / PAIR_ --, BK = 64):
 //   warp 0      TMA producer: cp.async.bulk.tensor.2d into a 5-stage ring, mbarrier expect_tx
 //   warp 1      MMA issuer: one elected lane issues 4 x tcgen05.mma (M128 N128 K16) per stage,
 //               tcgen05.commit releases the stage / publishes the accumulator; owns TMEM alloc
