@@ -1,4 +1,6 @@
 #!/bin/bash
+# (EDGEDICT_GEMM_PAIR_LSE / EDGEDICT_GEMM_PAIR_NKB existed only for this A/B; the committed policy is in gemm_tc.cu: logits+LSE and
+#  d-hidden on pair tiles automatically, split-K weight gradients only with eb_gemm_pair_mode(1))
 # same-box A/B of the pair-tile policy: (LSE pair, dW2 pair) in {0,1}^2, twice
 for rep in 1 2; do for cfg in "1 4096" "0 4096" "1 99999999" "0 99999999"; do
 set -- $cfg
