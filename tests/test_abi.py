@@ -128,3 +128,13 @@ def test_entry_points_reject_bad_arguments_before_touching_the_device(built):
     assert L.eb_lstm_tc_fwd(None, p, None, None, p, p, p, p, None, None, p, 4, 3, 64, None) == 2
     assert L.eb_lstm_tc_fwd(p, p, None, None, p, p, p, p, None, None, p, 4, 0, 64, None) == 2     # T <= 0
     assert L.eb_lstm_tc_bwd(p, p, p, None, p, None, None, p, p, p, p, 4, 3, 96, None) == 2        # H % 64
+    import ctypes
+    lens = (ctypes.c_int * 9)(3, 3, 3, 3, 3, 3, 3, 3, 3)
+    assert L.eb_lstm_tc_bwd_chunks(p, p, p, None, p, None, None, p, p, p, p, 4, lens, 9, 64, None) == 2   # more than 8 chunks
+    assert L.eb_lstm_tc_bwd_chunks(p, p, p, None, p, None, None, p, p, p, p, 4, None, 2, 64, None) == 2   # no chunk lengths
+    lens0 = (ctypes.c_int * 2)(3, 0)
+    assert L.eb_lstm_tc_bwd_chunks(p, p, p, None, p, None, None, p, p, p, p, 4, lens0, 2, 64, None) == 2  # empty chunk
+    assert L.eb_lstm_tc_bwd_chunks(p, p, p, None, p, None, None, p, p, p, p, 4, lens, 2, 96, None) == 2   # H % 64
+    prev = L.eb_gemm_pair_mode(1)                                                    # policy switch: returns the previous mode
+    assert prev in (-1, 0, 1) and L.eb_gemm_pair_mode(0) == 1 and L.eb_gemm_pair_mode(prev) == 0
+    assert L.eb_gemm_pair_mode(prev) == prev
